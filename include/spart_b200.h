@@ -1,0 +1,153 @@
+/*
+ * spart_b200.h -- C ABI of libspart_b200.so, the B200 (sm_100a) implementation of the
+ * SPART forward model (BSM soil -> PROSPECT-5D/PRO leaf -> SAILH canopy -> SMAC atmosphere
+ * -> sensor bands) evaluated over large batches of parameter sets.
+ *
+ * The reference (wirrell/SPART-python) has no FFI layer: its boundary is the Python call
+ * surface `SPART(soilpar, leafbio, canopy, atm, angles, sensor, DOY).run()`
+ * (reference src/SPART/SPART.py:83-95, 162-269).  Each entry point below names the part of
+ * that surface it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, a negative SPART_E* code
+ *     for an argument error, or a positive cudaError_t value for a CUDA failure;
+ *     spart_last_error() returns a thread-local description of the last failure;
+ *   - no exception ever crosses this boundary;
+ *   - `*_dev` pointers are device pointers owned by the caller (e.g. PyTorch's caching
+ *     allocator); the library never allocates per call on the device paths and all work is
+ *     enqueued asynchronously on the caller's stream (a cudaStream_t passed as void*);
+ *   - a context is immutable after spart_create and may be used concurrently from several
+ *     host threads; create one context per GPU;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Batch parameter layout ("params"): struct-of-arrays, double, [SPART_NPAR][ld] with
+ * ld >= n, row order
+ *   0..8   leaf    Cab Cdm Cw Cs Cca Cant N PROT CBC   (LeafBiology, prospect_5d.py:73-81)
+ *   9..14  soil    B lat lon SMp SMC film              (SoilParameters, bsm.py:269-287)
+ *   15..18 canopy  LAI LIDFa LIDFb q                   (CanopyStructure, sailh.py:340-348)
+ *   19..21 angles  sol_angle obs_angle rel_angle, deg  (Angles, sailh.py:298-301)
+ *   22..25 atm     aot550 uo3 uh2o Pa                  (AtmosphericProperties, smac.py:307-317)
+ *   26     DOY                                         (SPART.__init__, SPART.py:83)
+ */
+#ifndef SPART_B200_H
+#define SPART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPART_ABI_VERSION 1
+
+#define SPART_NPAR 27       /* rows of a parameter batch                                   */
+#define SPART_NWL 2001      /* 400..2400 nm, 1 nm (SpectralBands.wlP, SPART.py:303)        */
+#define SPART_NWL_S 2162    /* + 161 thermal wavelengths (SpectralBands.wlS, SPART.py:310) */
+#define SPART_NLC 17        /* per-wavelength constants, see SpartTables                   */
+#define SPART_NSMAC 60      /* per-band host-folded SMAC constants, see SpartSensor        */
+#define SPART_NOUT 3        /* R_TOC, R_TOA, L_TOA                                         */
+#define SPART_NSPEC 9       /* planes of spart_forward_spectrum                            */
+
+enum {
+  SPART_OK = 0,
+  SPART_EINVAL = -1,   /* bad argument (null pointer, negative size, unknown sensor index) */
+  SPART_ENODEV = -2,   /* no usable CUDA device                                            */
+  SPART_ENOMEM = -3    /* host allocation failed                                           */
+};
+
+enum { SPART_FP64 = 64, SPART_FP32 = 32 };
+
+typedef struct SpartCtx SpartCtx;
+
+/* Sample-independent per-wavelength constants, host pointer, double [SPART_NLC][SPART_NWL]:
+ *   0 Kab 1 Kca 2 Kdm 3 Kw 4 Ks 5 Kant 6 cbc 7 prot          optical_params.pkl (SPART.py:399-406)
+ *   8 tav(40,nr)  9 tav(90,nr)  10 tav(90,nr)/nr^2            prospect_5d.py:200-205
+ *   11..13 GSV[:,0..2]                                         bsm.py:45-52
+ *   14 tav(90,2/nw)/tav(90,2)  15 1-tav(90,nw)/nw^2  16 1-tav(40,nw)   bsm.py:110-119
+ * calculate_tav (prospect_5d.py:249-311) only ever receives table arguments, so these are
+ * folded once on the host. */
+typedef struct {
+  int32_t n_wl;            /* must be SPART_NWL */
+  const double* lc;        /* [SPART_NLC][n_wl] */
+} SpartTables;
+
+/* One sensor = the content of sensor_information/<name>.pkl the hot path uses
+ * (SPART.py:216-232, 358-396), with sample-independent sub-expressions folded on the host. */
+typedef struct {
+  int32_t n_bands;
+  const int32_t* wl_lo;    /* [n_bands] index into 400..2400 nm of the knot at/below wl_smac      */
+  const int32_t* wl_hi;    /* [n_bands] upper knot (== wl_lo when wl_smac hits a knot exactly)     */
+  const double* wl_frac;   /* [n_bands] wl_smac - knot(wl_lo): np.interp weight (SPART.py:220-223) */
+  const double* smac;      /* [SPART_NSMAC][n_bands] folded SMAC coefficients (smac.py:44-92)      */
+  const double* conv_ea;   /* [n_bands] SRF-convolved Ea (SPART.py:358-396 applied to ETpar['Ea']) */
+} SpartSensor;
+
+/* ABI version of the loaded library (== SPART_ABI_VERSION of the header it was built from). */
+int spart_abi_version(void);
+
+/* Thread-local text of the last error returned on this thread ("" if none). */
+const char* spart_last_error(void);
+
+/* Number of CUDA devices visible (0 when there is no driver/GPU). Never fails. */
+int spart_device_count(void);
+
+/* Replaces SPART.__init__'s table loads (SPART.py:92-95): uploads the immutable tables and
+ * all sensors to `device` once.  *out must be released with spart_destroy. */
+int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t n_sensors,
+                 int32_t device, SpartCtx** out);
+int spart_destroy(SpartCtx* ctx);
+
+/* Device scratch the caller must provide to the *_dev entry points for a batch of n samples. */
+size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n);
+
+/* Replaces the per-sample loop over SPART(...).run() (SPART.py:162-269): for every sample
+ * s < n and band b of sensor `sensor`, out_dev[(s * n_bands + b) * 3 + {0,1,2}] =
+ * {R_TOC, R_TOA, L_TOA}.  params_dev: [SPART_NPAR][ld] (see top).  precision: SPART_FP64 or
+ * SPART_FP32 (arithmetic type of the spectral/atmosphere stage; I/O is always double).
+ * Asynchronous on `stream`. */
+int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* params_dev,
+                        int64_t n, int64_t ld, int32_t precision, void* workspace_dev,
+                        double* out_dev, void* stream);
+
+/* Same computation with HOST buffers: params_host [SPART_NPAR][ld] and out_host
+ * [n][n_bands][3] are ordinary (pageable or pinned) host memory; the call stages them
+ * through internal pinned buffers in chunks, overlapping H2D, kernels and D2H on internal
+ * streams, and returns when out_host is complete.  This is the drop-in for a caller that
+ * holds NumPy arrays. */
+int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params_host,
+                             int64_t n, int64_t ld, int32_t precision, double* out_host);
+
+/* Replaces the leafopt / soilopt / canopyopt attributes of a SPART object after run()
+ * (SPART.py:192-214, 427-470): full 2162-wavelength spectra.
+ * out_dev: double [n][SPART_NSPEC][SPART_NWL_S], planes
+ *   0 leaf refl  1 leaf tran  2 kChlrel (0 beyond 2400 nm)  3 soil refl (wet)  4 soil refl dry
+ *   (value at 2400 nm beyond)  5 rso  6 rdo  7 rsd  8 rdd. */
+int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
+                           void* workspace_dev, double* out_dev, void* stream);
+
+/* Replaces CanopyStructure.__init__'s calculate_leafangles (sailh.py:340-398): the 13-class
+ * leaf inclination distribution for n (LIDFa, LIDFb) pairs.  ab_dev: double [2][ld];
+ * out_dev: double [n][13].  Needs no context. */
+int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_dev, void* stream);
+
+/* Per-kernel timing of spart_forward_bands with CUDA events recorded on the caller's stream
+ * (used by bench.py for the roofline).  After spart_profile_enable(ctx, 1) every
+ * spart_forward_bands call records three events around its two kernels; spart_profile_read
+ * waits for them and returns the summed durations [ms] of the per-sample kernel and of the
+ * per-(sample, band) kernel over `*calls` calls, then clears the list. */
+int spart_profile_enable(SpartCtx* ctx, int32_t on);
+int spart_profile_read(SpartCtx* ctx, double* sample_ms, double* band_ms, int64_t* calls);
+
+/* Micro-benchmarks used as roofline denominators by bench.py: dependent-free DFMA / FFMA
+ * chains on all SMs.  Results in TFLOP/s (FMA = 2 flop). */
+int spart_measure_peaks(int32_t device, double* fp64_tflops, double* fp32_tflops);
+
+/* Number of kernel launches this library has enqueued on this thread since load. */
+int64_t spart_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPART_B200_H */

@@ -1,0 +1,684 @@
+// spart_kernels.cu -- sm_100a kernels and the C ABI of libspart_b200.so.
+//
+// Data flow for one batch (all buffers in HBM, struct-of-arrays over samples so that every
+// warp-wide access is one or two fully used 128-byte lines):
+//
+//   params [27][n]  --sample_kernel-->  rec [R_COUNT][n]   (one thread per sample:
+//        leaf-angle distribution, 13-class volume scattering, hot-spot integrals, soil
+//        vector weights, SMAC geometry/pressure scalars, ET scale)
+//   params + rec    --band_kernel---->  out [n][nb][3]      (one thread per (sample, band):
+//        PROSPECT + BSM + SAILH at the 1-2 wavelengths np.interp touches, SMAC, TOC->TOA)
+//   params + rec    --spectrum_kernel-> spec [n][9][2162]   (leafopt/soilopt/canopyopt)
+//
+// In band_kernel / spectrum_kernel all lanes of a warp work on the same wavelength, so the
+// per-wavelength and per-band constants are warp-uniform shared-memory broadcasts and the
+// arithmetic is pure FP64-pipe work; see DESIGN.md for the roofline of each kernel.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/spart_b200.h"
+#include "spart_device.cuh"
+
+using namespace spart;
+
+static_assert(LC_COUNT == SPART_NLC, "LC layout");
+static_assert(SM_COUNT == SPART_NSMAC, "SMAC layout");
+static_assert(SM_USED <= SM_COUNT, "SMAC layout");
+static_assert(P_COUNT == SPART_NPAR, "param layout");
+
+// --------------------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+static int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof(g_err), fmt, detail);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      snprintf(g_err, sizeof(g_err), "%s failed: %s", #expr, cudaGetErrorString(_e));    \
+      return (int)_e;                                                                    \
+    }                                                                                    \
+  } while (0)
+
+// --------------------------------------------------------------------------------------
+// device-side band table: one row of BT_COUNT doubles per band
+// --------------------------------------------------------------------------------------
+enum BandTableCol {
+  BT_SMAC = 0,                    // SM_COUNT folded SMAC constants
+  BT_CONVEA = SM_COUNT,           // SRF-convolved extraterrestrial irradiance
+  BT_FRAC,                        // np.interp offset (0 => single knot)
+  BT_NPTS,                        // 1 or 2 wavelengths to evaluate
+  BT_PAD,
+  BT_LC0,                         // LC_COUNT constants at the lower knot
+  BT_LC1 = BT_LC0 + LC_COUNT,     // LC_COUNT constants at the upper knot
+  BT_COUNT = BT_LC1 + LC_COUNT
+};
+
+__constant__ double c_sin_ttli[13];
+__constant__ double c_cos_ttli[13];
+
+struct SpartCtx {
+  int device = 0;
+  int n_sensors = 0;
+  int sm_count = 0;
+  double* d_lc = nullptr;               // [LC_COUNT][SPART_NWL]
+  std::vector<double*> d_band;          // per sensor [nb][BT_COUNT]
+  std::vector<int> n_bands;
+  // host-buffer path: lazily created staging slots
+  std::mutex mu;
+  static const int kSlots = 3;
+  cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
+  double* slot_params[kSlots] = {nullptr, nullptr, nullptr};
+  double* slot_rec[kSlots] = {nullptr, nullptr, nullptr};
+  double* slot_out[kSlots] = {nullptr, nullptr, nullptr};
+  int64_t slot_cap = 0;      // samples per slot
+  int64_t slot_out_cap = 0;  // doubles of output per slot
+  // optional per-kernel timing of spart_forward_bands (spart_profile_enable / _read)
+  mutable std::mutex prof_mu;
+  mutable bool profiling = false;
+  struct ProfEvents { cudaEvent_t e[3]; };
+  mutable std::vector<ProfEvents> prof_pending;
+  mutable std::vector<ProfEvents> prof_free;
+};
+
+// --------------------------------------------------------------------------------------
+// kernels
+// --------------------------------------------------------------------------------------
+constexpr int kSampleThreads = 128;
+
+// One thread per sample: everything that does not depend on wavelength or band.
+__global__ void __launch_bounds__(kSampleThreads)
+sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec) {
+  __shared__ double sF[12][kSampleThreads];
+  const int64_t s = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
+  if (s >= n) return;
+  const int tid = threadIdx.x;
+
+  // leaf inclination distribution (CanopyStructure.__init__, sailh.py:340-398)
+  lidf_cumulative(P[P_LIDFA * ld + s], P[P_LIDFB * ld + s], &sF[0][tid], kSampleThreads);
+
+  // sun / observer geometry (sailh.py:59-78)
+  const double tts = P[P_SZA * ld + s], tto = P[P_VZA * ld + s], rel = P[P_RAA * ld + s];
+  const double psi = fabs(rel - 360.0 * rint(rel / 360.0));
+  const double psi_rad = psi * SPART_DEG2RAD;
+  double sin_tts, cos_tts, sin_tto, cos_tto;
+  sincos(tts * SPART_DEG2RAD, &sin_tts, &cos_tts);
+  sincos(tto * SPART_DEG2RAD, &sin_tto, &cos_tto);
+  const double tan_tts = tan(tts * SPART_DEG2RAD), tan_tto = tan(tto * SPART_DEG2RAD);
+  const double cos_psi = cos(psi_rad);
+  const double dso = sqrt(tan_tts * tan_tts + tan_tto * tan_tto - 2.0 * tan_tts * tan_tto * cos_psi);
+
+  // 13 leaf-inclination classes, dotted with lidf (sailh.py:81-97)
+  double k = 0.0, K = 0.0, bf = 0.0, sob = 0.0, sof = 0.0;
+  const double inv_cc = SPART_PI / (cos_tts * cos_tto);
+  double Fprev = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < 13; ++i) {
+    const double Fi = (i < 12) ? sF[i][tid] : 1.0;
+    const double lidf = Fi - Fprev;
+    Fprev = Fi;
+    double chi_s, chi_o, frho, ftau;
+    volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
+                   chi_o, frho, ftau);
+    k += (chi_s / cos_tts) * lidf;
+    K += (chi_o / cos_tto) * lidf;
+    bf += (c_cos_ttli[i] * c_cos_ttli[i]) * lidf;
+    sob += (frho * inv_cc) * lidf;
+    sof += (ftau * inv_cc) * lidf;
+  }
+
+  const double LAI = P[P_LAI * ld + s], q = P[P_Q * ld + s];
+  double sumpso, pso2w;
+  hotspot_integrals(K, k, LAI, q, dso, sumpso, pso2w);
+
+  rec[R_K_SUN * n + s] = k;
+  rec[R_K_OBS * n + s] = K;
+  rec[R_BF * n + s] = bf;
+  rec[R_SOB * n + s] = sob;
+  rec[R_SOF * n + s] = sof;
+  rec[R_TAUSS * n + s] = exp(-k * LAI);
+  rec[R_TAUOO * n + s] = exp(-K * LAI);
+  rec[R_SUMPSO * n + s] = sumpso;
+  rec[R_PSO2W * n + s] = pso2w;
+
+  // BSM soil-vector weights and Poisson mean (bsm.py:49-51, 101)
+  {
+    const double B = P[P_B * ld + s];
+    double slat, clat, slon, clon;
+    sincos(P[P_LAT * ld + s] * SPART_PI / 180.0, &slat, &clat);
+    sincos(P[P_LON * ld + s] * SPART_PI / 180.0, &slon, &clon);
+    rec[R_F1 * n + s] = B * slat;
+    rec[R_F2 * n + s] = B * clat * slon;
+    rec[R_F3 * n + s] = B * clat * clon;
+    const double mu = (P[P_SMP * ld + s] - 5.0) / P[P_SMC * ld + s];
+    rec[R_MU * n + s] = mu;
+    rec[R_EMU * n + s] = exp(-mu);
+  }
+
+  // SMAC per-sample scalars (smac.py:98-102, 129-141)
+  {
+    const double us = cos_tts, uv = cos_tto;    // cos(tts*cdr), cos(tto*cdr)
+    const double Peq = P[P_PA * ld + s] / 1013.25;
+    const double m = 1.0 / us + 1.0 / uv;
+    const double crd = 180.0 / SPART_PI;
+    double cksi = -((us * uv) + (sqrt(1.0 - us * us) * sqrt(1.0 - uv * uv) * cos(rel * crd)));
+    if (cksi < -1.0) cksi = -1.0;
+    const double ksiD = crd * acos(cksi);
+    rec[R_US * n + s] = us;
+    rec[R_UV * n + s] = uv;
+    rec[R_M * n + s] = m;
+    rec[R_PEQ * n + s] = Peq;
+    rec[R_LO3 * n + s] = log(P[P_UO3 * ld + s] * m);
+    rec[R_LH2O * n + s] = log(P[P_UH2O * ld + s] * m);
+    rec[R_LM * n + s] = log(m);
+    rec[R_LPEQ * n + s] = log(Peq);
+    rec[R_CKSI * n + s] = cksi;
+    rec[R_KSID * n + s] = ksiD;
+    rec[R_RAYPH * n + s] = 0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742;
+    // extraterrestrial radiance scale (SPART.py:345-353)
+    const double b = 2.0 * SPART_PI * P[P_DOY * ld + s] / 365.0;
+    double sb, cb, s2b, c2b;
+    sincos(b, &sb, &cb);
+    sincos(2.0 * b, &s2b, &c2b);
+    const double cf = 1.00011 + 0.034221 * cb + 0.00128 * sb + 0.000719 * c2b + 0.000077 * s2b;
+    rec[R_ETSCALE * n + s] = cf * us / SPART_PI;
+  }
+}
+
+__device__ __forceinline__ CanopyGeo load_geo(const double* __restrict__ P, int64_t ld,
+                                              const double* __restrict__ rec, int64_t n, int64_t s) {
+  CanopyGeo G;
+  G.LAI = P[P_LAI * ld + s];
+  G.k = rec[R_K_SUN * n + s];
+  G.K = rec[R_K_OBS * n + s];
+  G.bf = rec[R_BF * n + s];
+  G.sob = rec[R_SOB * n + s];
+  G.sof = rec[R_SOF * n + s];
+  G.tau_ss = rec[R_TAUSS * n + s];
+  G.tau_oo = rec[R_TAUOO * n + s];
+  G.sumpso = rec[R_SUMPSO * n + s];
+  G.pso2w = rec[R_PSO2W * n + s];
+  return G;
+}
+
+__device__ __forceinline__ SoilPar load_soil(const double* __restrict__ P, int64_t ld,
+                                             const double* __restrict__ rec, int64_t n, int64_t s) {
+  SoilPar S;
+  S.f1 = rec[R_F1 * n + s];
+  S.f2 = rec[R_F2 * n + s];
+  S.f3 = rec[R_F3 * n + s];
+  S.mu = rec[R_MU * n + s];
+  S.emu = rec[R_EMU * n + s];
+  S.film = P[P_FILM * ld + s];
+  return S;
+}
+
+constexpr int kBandThreads = 128;
+
+// One thread per (sample, band); blockIdx.x = band (fastest, so the blocks that share a
+// sample tile run together and re-use it from L2), blockIdx.y = sample tile.
+__global__ void __launch_bounds__(kBandThreads)
+band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+            const double* __restrict__ band_table, int nb, double* __restrict__ out) {
+  __shared__ TauTable s_tau;
+  __shared__ double s_bt[BT_COUNT];
+  const int b = blockIdx.x;
+  load_tau_table(&s_tau);
+  for (int i = threadIdx.x; i < BT_COUNT; i += blockDim.x) s_bt[i] = band_table[(size_t)b * BT_COUNT + i];
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
+  if (s >= n) return;
+
+  const LeafPar L = load_leaf(P, ld, s);
+  const SoilPar S = load_soil(P, ld, rec, n, s);
+  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+
+  double rso, rdo, rsd, rdd;
+  {
+    double refl, tran, kchl, rwet, rdry;
+    prospect_point(L, &s_bt[BT_LC0], &s_tau, refl, tran, kchl);
+    bsm_point(S, &s_bt[BT_LC0], rwet, rdry);
+    sailh_point(G, refl, tran, rwet, rso, rdo, rsd, rdd);
+  }
+  if (s_bt[BT_NPTS] > 1.5) {  // band centre between two knots: np.interp (SPART.py:220-223)
+    double refl, tran, kchl, rwet, rdry, rso1, rdo1, rsd1, rdd1;
+    prospect_point(L, &s_bt[BT_LC1], &s_tau, refl, tran, kchl);
+    bsm_point(S, &s_bt[BT_LC1], rwet, rdry);
+    sailh_point(G, refl, tran, rwet, rso1, rdo1, rsd1, rdd1);
+    const double fr = s_bt[BT_FRAC];
+    rso = (rso1 - rso) * fr + rso;
+    rdo = (rdo1 - rdo) * fr + rdo;
+    rsd = (rsd1 - rsd) * fr + rsd;
+    rdd = (rdd1 - rdd) * fr + rdd;
+  }
+
+  AtmSample A;
+  A.us = rec[R_US * n + s];
+  A.uv = rec[R_UV * n + s];
+  A.m = rec[R_M * n + s];
+  A.Peq = rec[R_PEQ * n + s];
+  A.lo3 = rec[R_LO3 * n + s];
+  A.lh2o = rec[R_LH2O * n + s];
+  A.lm = rec[R_LM * n + s];
+  A.lpeq = rec[R_LPEQ * n + s];
+  A.cksi = rec[R_CKSI * n + s];
+  A.ksiD = rec[R_KSID * n + s];
+  A.ray_phase = rec[R_RAYPH * n + s];
+  A.taup550 = P[P_AOT * ld + s];
+
+  double R_TOC, R_TOA, L_TOA;
+  smac_toa_band(A, &s_bt[BT_SMAC], s_bt[BT_CONVEA], rec[R_ETSCALE * n + s], rso, rdo, rdd, rsd, R_TOC, R_TOA,
+                L_TOA);
+  double* o = out + ((size_t)s * nb + b) * SPART_NOUT;
+  o[0] = R_TOC;
+  o[1] = R_TOA;
+  o[2] = L_TOA;
+}
+
+// Full-spectrum planes: blockIdx.x = chunk of kSpecChunk wavelengths, blockIdx.y = sample tile.
+constexpr int kSpecThreads = 128;
+constexpr int kSpecChunk = 32;
+
+__global__ void __launch_bounds__(kSpecThreads)
+spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+                const double* __restrict__ lc_table, double* __restrict__ out) {
+  __shared__ TauTable s_tau;
+  __shared__ double s_lc[kSpecChunk][LC_COUNT];
+  const int w0 = blockIdx.x * kSpecChunk;
+  load_tau_table(&s_tau);
+  for (int i = threadIdx.x; i < kSpecChunk * LC_COUNT; i += blockDim.x) {
+    const int w = w0 + i / LC_COUNT, r = i % LC_COUNT;
+    // thermal wavelengths re-use the 2400 nm soil constants (SPART.py:440)
+    s_lc[i / LC_COUNT][r] = lc_table[(size_t)r * SPART_NWL + min(w, SPART_NWL - 1)];
+  }
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.y * kSpecThreads + threadIdx.x;
+  if (s >= n) return;
+  const LeafPar L = load_leaf(P, ld, s);
+  const SoilPar S = load_soil(P, ld, rec, n, s);
+  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+  double* o = out + (size_t)s * SPART_NSPEC * SPART_NWL_S;
+  for (int j = 0; j < kSpecChunk; ++j) {
+    const int w = w0 + j;
+    if (w >= SPART_NWL_S) break;
+    double refl, tran, kchl, rwet, rdry, rso, rdo, rsd, rdd;
+    bsm_point(S, s_lc[j], rwet, rdry);
+    if (w < SPART_NWL) {
+      prospect_point(L, s_lc[j], &s_tau, refl, tran, kchl);
+    } else {  // thermal assumptions (SPART.py:461-466; LeafBiology rho/tau_thermal = 0.01)
+      refl = 0.01;
+      tran = 0.01;
+      kchl = 0.0;
+    }
+    sailh_point(G, refl, tran, rwet, rso, rdo, rsd, rdd);
+    o[0 * SPART_NWL_S + w] = refl;
+    o[1 * SPART_NWL_S + w] = tran;
+    o[2 * SPART_NWL_S + w] = kchl;
+    o[3 * SPART_NWL_S + w] = rwet;
+    o[4 * SPART_NWL_S + w] = rdry;
+    o[5 * SPART_NWL_S + w] = rso;
+    o[6 * SPART_NWL_S + w] = rdo;
+    o[7 * SPART_NWL_S + w] = rsd;
+    o[8 * SPART_NWL_S + w] = rdd;
+  }
+}
+
+// Leaf inclination distribution only (CanopyStructure.lidf, sailh.py:340-398).
+__global__ void __launch_bounds__(kSampleThreads)
+leafangles_kernel(const double* __restrict__ ab, int64_t n, int64_t ld, double* __restrict__ out) {
+  __shared__ double sF[12][kSampleThreads];
+  const int64_t s = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
+  if (s >= n) return;
+  const int tid = threadIdx.x;
+  lidf_cumulative(ab[s], ab[ld + s], &sF[0][tid], kSampleThreads);
+  double Fprev = 0.0;
+  for (int i = 0; i < 13; ++i) {
+    const double Fi = (i < 12) ? sF[i][tid] : 1.0;
+    out[(size_t)s * 13 + i] = Fi - Fprev;
+    Fprev = Fi;
+  }
+}
+
+// ---- peak micro-benchmarks ---------------------------------------------------------------
+template <typename T>
+__global__ void fma_chain_kernel(T* out, int iters, T a, T b) {
+  T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+    x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+    x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+  }
+  T r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (r == (T)-12345.678) out[0] = r;   // never true; keeps the chain alive
+}
+
+template <typename T>
+static int time_fma(int sm_count, double* tflops) {
+  T* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(T)));
+  const int iters = 1 << 14, threads = 512, blocks = sm_count * 8;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    fma_chain_kernel<T><<<blocks, threads>>>(d, iters, (T)1.0000001, (T)1e-7);
+    ++g_launches;
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return SPART_OK;
+}
+
+// --------------------------------------------------------------------------------------
+// C ABI
+// --------------------------------------------------------------------------------------
+extern "C" {
+
+int spart_abi_version(void) { return SPART_ABI_VERSION; }
+const char* spart_last_error(void) { return g_err; }
+int64_t spart_launch_count(void) { return g_launches; }
+
+int spart_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t n_sensors, int32_t device,
+                 SpartCtx** out) {
+  if (!tables || !tables->lc || !out || n_sensors < 0 || (n_sensors > 0 && !sensors))
+    return fail(SPART_EINVAL, "spart_create: null argument%s");
+  if (tables->n_wl != SPART_NWL) return fail(SPART_EINVAL, "spart_create: tables->n_wl must be 2001%s");
+  int ndev = spart_device_count();
+  if (ndev <= 0) return fail(SPART_ENODEV, "spart_create: no CUDA device (this library has no CPU fallback)%s");
+  if (device < 0 || device >= ndev) return fail(SPART_EINVAL, "spart_create: device index out of range%s");
+  for (int i = 0; i < n_sensors; ++i) {
+    const SpartSensor& S = sensors[i];
+    if (S.n_bands <= 0 || !S.wl_lo || !S.wl_hi || !S.wl_frac || !S.smac || !S.conv_ea)
+      return fail(SPART_EINVAL, "spart_create: incomplete sensor%s");
+    for (int b = 0; b < S.n_bands; ++b)
+      if (S.wl_lo[b] < 0 || S.wl_lo[b] >= SPART_NWL || S.wl_hi[b] < S.wl_lo[b] || S.wl_hi[b] >= SPART_NWL)
+        return fail(SPART_EINVAL, "spart_create: band knot outside 400..2400 nm%s");
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  SpartCtx* ctx = new (std::nothrow) SpartCtx();
+  if (!ctx) return fail(SPART_ENOMEM, "spart_create: out of host memory%s");
+  ctx->device = device;
+  ctx->n_sensors = n_sensors;
+  CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+
+  CUDA_TRY(cudaMemcpyToSymbol(c_tau_coef, SPART_TAU_COEF_H, sizeof(SPART_TAU_COEF_H)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_tau_mid, SPART_TAU_MID_H, sizeof(SPART_TAU_MID_H)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_tau_invhalf, SPART_TAU_INVHALF_H, sizeof(SPART_TAU_INVHALF_H)));
+  double sl[13], cl[13];
+  for (int i = 0; i < 13; ++i) {  // litab (sailh.py:49): 5,15,...,75, 81,83,...,89 degrees
+    const double li = (i < 8) ? 5.0 + 10.0 * i : 81.0 + 2.0 * (i - 8);
+    sl[i] = sin(li * (M_PI / 180.0));
+    cl[i] = cos(li * (M_PI / 180.0));
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(c_sin_ttli, sl, sizeof(sl)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_cos_ttli, cl, sizeof(cl)));
+
+  const size_t lc_bytes = sizeof(double) * LC_COUNT * SPART_NWL;
+  CUDA_TRY(cudaMalloc(&ctx->d_lc, lc_bytes));
+  CUDA_TRY(cudaMemcpy(ctx->d_lc, tables->lc, lc_bytes, cudaMemcpyHostToDevice));
+
+  for (int i = 0; i < n_sensors; ++i) {
+    const SpartSensor& S = sensors[i];
+    std::vector<double> bt((size_t)S.n_bands * BT_COUNT, 0.0);
+    for (int b = 0; b < S.n_bands; ++b) {
+      double* row = &bt[(size_t)b * BT_COUNT];
+      for (int r = 0; r < SM_COUNT; ++r) row[BT_SMAC + r] = S.smac[(size_t)r * S.n_bands + b];
+      row[BT_CONVEA] = S.conv_ea[b];
+      row[BT_FRAC] = S.wl_frac[b];
+      row[BT_NPTS] = (S.wl_hi[b] != S.wl_lo[b]) ? 2.0 : 1.0;
+      for (int r = 0; r < LC_COUNT; ++r) {
+        row[BT_LC0 + r] = tables->lc[(size_t)r * SPART_NWL + S.wl_lo[b]];
+        row[BT_LC1 + r] = tables->lc[(size_t)r * SPART_NWL + S.wl_hi[b]];
+      }
+    }
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, bt.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(d, bt.data(), bt.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->d_band.push_back(d);
+    ctx->n_bands.push_back(S.n_bands);
+  }
+  *out = ctx;
+  return SPART_OK;
+}
+
+int spart_destroy(SpartCtx* ctx) {
+  if (!ctx) return SPART_OK;
+  cudaSetDevice(ctx->device);
+  for (int i = 0; i < SpartCtx::kSlots; ++i) {
+    if (ctx->streams[i]) cudaStreamSynchronize(ctx->streams[i]);
+    if (ctx->slot_params[i]) cudaFree(ctx->slot_params[i]);
+    if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
+    if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+  }
+  for (auto& pe : ctx->prof_pending) for (int i = 0; i < 3; ++i) cudaEventDestroy(pe.e[i]);
+  for (auto& pe : ctx->prof_free) for (int i = 0; i < 3; ++i) cudaEventDestroy(pe.e[i]);
+  for (double* d : ctx->d_band) cudaFree(d);
+  if (ctx->d_lc) cudaFree(ctx->d_lc);
+  delete ctx;
+  return SPART_OK;
+}
+
+size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n) {
+  (void)ctx;
+  if (n < 0) return 0;
+  return sizeof(double) * (size_t)R_COUNT * (size_t)n;
+}
+
+static int launch_sample(const double* params_dev, int64_t n, int64_t ld, double* rec, cudaStream_t st) {
+  const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+  sample_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, rec);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return SPART_OK;
+}
+
+static int check_batch(const SpartCtx* ctx, const void* params, int64_t n, int64_t ld, const void* ws,
+                       const void* out, const char* who) {
+  if (!ctx || !params || !out || (!ws && n > 0)) return fail(SPART_EINVAL, "%s: null argument", who);
+  if (n < 0 || ld < n) return fail(SPART_EINVAL, "%s: need 0 <= n <= ld", who);
+  if (n > (int64_t)65535 * kBandThreads)
+    return fail(SPART_EINVAL, "%s: n exceeds 65535*128 samples per call; split the batch", who);
+  return SPART_OK;
+}
+
+int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* params_dev, int64_t n, int64_t ld,
+                        int32_t precision, void* workspace_dev, double* out_dev, void* stream) {
+  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_forward_bands");
+  if (rc) return rc;
+  if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "spart_forward_bands: unknown sensor%s");
+  if (precision != SPART_FP64)
+    return fail(SPART_EINVAL, "spart_forward_bands: only SPART_FP64 is implemented in this build%s");
+  if (n == 0) return SPART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* rec = (double*)workspace_dev;
+  SpartCtx::ProfEvents pe;
+  bool prof = false;
+  {
+    std::lock_guard<std::mutex> lock(ctx->prof_mu);
+    if (ctx->profiling) {
+      prof = true;
+      if (!ctx->prof_free.empty()) {
+        pe = ctx->prof_free.back();
+        ctx->prof_free.pop_back();
+      } else {
+        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&pe.e[i]));
+      }
+    }
+  }
+  if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
+  rc = launch_sample(params_dev, n, ld, rec, st);
+  if (rc) return rc;
+  if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
+  const int nb = ctx->n_bands[sensor];
+  dim3 grid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
+  band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  if (prof) {
+    CUDA_TRY(cudaEventRecord(pe.e[2], st));
+    std::lock_guard<std::mutex> lock(ctx->prof_mu);
+    ctx->prof_pending.push_back(pe);
+  }
+  return SPART_OK;
+}
+
+int spart_profile_enable(SpartCtx* ctx, int32_t on) {
+  if (!ctx) return fail(SPART_EINVAL, "spart_profile_enable: null context%s");
+  std::lock_guard<std::mutex> lock(ctx->prof_mu);
+  ctx->profiling = on != 0;
+  for (auto& pe : ctx->prof_pending) ctx->prof_free.push_back(pe);
+  ctx->prof_pending.clear();
+  return SPART_OK;
+}
+
+int spart_profile_read(SpartCtx* ctx, double* sample_ms, double* band_ms, int64_t* calls) {
+  if (!ctx || !sample_ms || !band_ms || !calls) return fail(SPART_EINVAL, "spart_profile_read: null argument%s");
+  std::lock_guard<std::mutex> lock(ctx->prof_mu);
+  double a = 0.0, b = 0.0;
+  for (auto& pe : ctx->prof_pending) {
+    CUDA_TRY(cudaEventSynchronize(pe.e[2]));
+    float m0 = 0.f, m1 = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&m0, pe.e[0], pe.e[1]));
+    CUDA_TRY(cudaEventElapsedTime(&m1, pe.e[1], pe.e[2]));
+    a += m0;
+    b += m1;
+    ctx->prof_free.push_back(pe);
+  }
+  *sample_ms = a;
+  *band_ms = b;
+  *calls = (int64_t)ctx->prof_pending.size();
+  ctx->prof_pending.clear();
+  return SPART_OK;
+}
+
+int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
+                           void* workspace_dev, double* out_dev, void* stream) {
+  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_forward_spectrum");
+  if (rc) return rc;
+  if (n == 0) return SPART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* rec = (double*)workspace_dev;
+  rc = launch_sample(params_dev, n, ld, rec, st);
+  if (rc) return rc;
+  dim3 grid((SPART_NWL_S + kSpecChunk - 1) / kSpecChunk, (unsigned)((n + kSpecThreads - 1) / kSpecThreads));
+  spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, out_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return SPART_OK;
+}
+
+int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_dev, void* stream) {
+  if (!ab_dev || !out_dev) return fail(SPART_EINVAL, "spart_leafangles: null argument%s");
+  if (n < 0 || ld < n) return fail(SPART_EINVAL, "spart_leafangles: need 0 <= n <= ld%s");
+  if (n == 0) return SPART_OK;
+  const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+  leafangles_kernel<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(ab_dev, n, ld, out_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return SPART_OK;
+}
+
+static int ensure_slots(SpartCtx* ctx, int64_t chunk, int nb) {
+  const int64_t out_need = chunk * nb * SPART_NOUT;
+  if (ctx->slot_cap >= chunk && ctx->slot_out_cap >= out_need) return SPART_OK;
+  for (int i = 0; i < SpartCtx::kSlots; ++i) {
+    if (!ctx->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamSynchronize(ctx->streams[i]));
+    if (ctx->slot_cap < chunk) {
+      if (ctx->slot_params[i]) cudaFree(ctx->slot_params[i]);
+      if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
+      ctx->slot_params[i] = ctx->slot_rec[i] = nullptr;
+      CUDA_TRY(cudaMalloc(&ctx->slot_params[i], sizeof(double) * P_COUNT * chunk));
+      CUDA_TRY(cudaMalloc(&ctx->slot_rec[i], sizeof(double) * R_COUNT * chunk));
+    }
+    if (ctx->slot_out_cap < out_need) {
+      if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
+      ctx->slot_out[i] = nullptr;
+      CUDA_TRY(cudaMalloc(&ctx->slot_out[i], sizeof(double) * out_need));
+    }
+  }
+  if (ctx->slot_cap < chunk) ctx->slot_cap = chunk;
+  if (ctx->slot_out_cap < out_need) ctx->slot_out_cap = out_need;
+  return SPART_OK;
+}
+
+int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params_host, int64_t n, int64_t ld,
+                             int32_t precision, double* out_host) {
+  if (!ctx || !params_host || !out_host) return fail(SPART_EINVAL, "spart_forward_bands_host: null argument%s");
+  if (n < 0 || ld < n) return fail(SPART_EINVAL, "spart_forward_bands_host: need 0 <= n <= ld%s");
+  if (sensor < 0 || sensor >= ctx->n_sensors)
+    return fail(SPART_EINVAL, "spart_forward_bands_host: unknown sensor%s");
+  if (precision != SPART_FP64)
+    return fail(SPART_EINVAL, "spart_forward_bands_host: only SPART_FP64 is implemented in this build%s");
+  if (n == 0) return SPART_OK;
+  std::lock_guard<std::mutex> lock(ctx->mu);
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int nb = ctx->n_bands[sensor];
+  // chunk so that three slots pipeline H2D / kernels / D2H; cap the per-slot output at ~256 MB
+  int64_t chunk = 1 << 18;
+  const int64_t cap_by_out = ((int64_t)256 << 20) / ((int64_t)nb * SPART_NOUT * 8);
+  if (chunk > cap_by_out) chunk = cap_by_out > 1024 ? cap_by_out : 1024;
+  if (chunk > n) chunk = n;
+  int rc = ensure_slots(ctx, chunk, nb);
+  if (rc) return rc;
+  int slot = 0;
+  for (int64_t s0 = 0; s0 < n; s0 += chunk, slot = (slot + 1) % SpartCtx::kSlots) {
+    const int64_t m = (n - s0 < chunk) ? (n - s0) : chunk;
+    cudaStream_t st = ctx->streams[slot];
+    // rows of the SoA batch are ld apart on the host and m apart in the slot
+    CUDA_TRY(cudaMemcpy2DAsync(ctx->slot_params[slot], sizeof(double) * m, params_host + s0, sizeof(double) * ld,
+                               sizeof(double) * m, P_COUNT, cudaMemcpyHostToDevice, st));
+    rc = spart_forward_bands(ctx, sensor, ctx->slot_params[slot], m, m, precision, ctx->slot_rec[slot],
+                             ctx->slot_out[slot], st);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)s0 * nb * SPART_NOUT, ctx->slot_out[slot],
+                             sizeof(double) * m * nb * SPART_NOUT, cudaMemcpyDeviceToHost, st));
+  }
+  for (int i = 0; i < SpartCtx::kSlots; ++i) CUDA_TRY(cudaStreamSynchronize(ctx->streams[i]));
+  return SPART_OK;
+}
+
+int spart_measure_peaks(int32_t device, double* fp64_tflops, double* fp32_tflops) {
+  if (!fp64_tflops || !fp32_tflops) return fail(SPART_EINVAL, "spart_measure_peaks: null argument%s");
+  if (spart_device_count() <= 0) return fail(SPART_ENODEV, "spart_measure_peaks: no CUDA device%s");
+  CUDA_TRY(cudaSetDevice(device));
+  int sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+  int rc = time_fma<double>(sm, fp64_tflops);
+  if (rc) return rc;
+  return time_fma<float>(sm, fp32_tflops);
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""Batched entry point: the drop-in for a loop over `SPART(...).run()`.
+
+    out = run_batch(leaf, soil, canopy, angles, atm, doy, "Sentinel2A-MSI")   # [n, nb, 3]
+
+replaces (reference src/SPART/SPART.py:83-95, 162-269)
+
+    for i in range(n):
+        out[i] = SPART(SoilParameters(*soil[i]), LeafBiology(*leaf[i]), CanopyStructure(*canopy[i]),
+                       AtmosphericProperties(*atm[i]), Angles(*angles[i]), sensor, doy[i]).run()[...]
+
+with one fresh model object per sample (the reference's dirty-flag cache is not reproduced,
+SURVEY.md section 3.2).
+"""
+import numpy as np
+import pandas as pd
+import torch
+
+from .engine import NPAR, default_engine
+
+_GROUPS = (("leaf", 9), ("soil", 6), ("canopy", 4), ("angles", 3), ("atm", 4), ("doy", 1))
+
+
+def pack_batch(leaf, soil, canopy, angles, atm, doy, device=None):
+    """Assemble the [27, n] float64 parameter block (layout of include/spart_b200.h).
+
+    leaf [n, 9] (or [n, 7]: PROT = CBC = 0), soil [n, 6] (or [n, 4]: SMC = 25, film = 0.015),
+    canopy [n, 4], angles [n, 3] or [3], atm [n, 4], doy [n] or scalar.  NumPy arrays give a
+    NumPy block, torch tensors give a torch block on `device` (or on the tensors' device).
+    """
+    use_torch = any(isinstance(x, torch.Tensor) for x in (leaf, soil, canopy, angles, atm, doy))
+    if use_torch:
+        dev = device
+        for x in (leaf, soil, canopy, angles, atm, doy):
+            if isinstance(x, torch.Tensor) and dev is None:
+                dev = x.device
+        as2d = lambda x: torch.as_tensor(x, dtype=torch.float64, device=dev).reshape(-1, 1) if (
+            torch.as_tensor(x).dim() <= 1) else torch.as_tensor(x, dtype=torch.float64, device=dev)
+        cat, full, empty = torch.cat, (lambda n, w, v: torch.full((n, w), v, dtype=torch.float64, device=dev)), None
+    else:
+        as2d = lambda x: np.asarray(x, dtype=np.float64).reshape(-1, 1) if np.ndim(x) <= 1 else np.asarray(
+            x, dtype=np.float64)
+        cat = lambda xs, dim: np.concatenate(xs, axis=dim)
+        full = lambda n, w, v: np.full((n, w), v, dtype=np.float64)
+
+    leaf, soil, canopy, atm = as2d(leaf), as2d(soil), as2d(canopy), as2d(atm)
+    n = leaf.shape[0]
+    if leaf.shape[1] == 7:
+        leaf = cat([leaf, full(n, 2, 0.0)], 1)
+    if soil.shape[1] == 4:
+        soil = cat([soil, full(n, 1, 25.0), full(n, 1, 0.015)], 1)
+    ang = as2d(angles)
+    if ang.shape[0] == 3 and ang.shape[1] == 1:          # shared geometry [3]
+        ang = ang.reshape(1, 3).expand(n, 3) if use_torch else np.broadcast_to(ang.reshape(1, 3), (n, 3))
+    d = as2d(doy)
+    if d.shape[0] == 1 and n != 1:
+        d = d.expand(n, 1) if use_torch else np.broadcast_to(d, (n, 1))
+    cols = [leaf, soil, canopy, ang, atm, d]
+    for (name, width), c in zip(_GROUPS, cols):
+        if c.shape != (n, width):
+            raise ValueError(f"{name}: expected shape ({n}, {width}), got {tuple(c.shape)}")
+    block = cat(cols, 1)                                   # [n, 27]
+    return block.t().contiguous() if use_torch else np.ascontiguousarray(block.T)
+
+
+def run_batch_params(params, sensor, precision="fp64", device=None, out=None):
+    """params: [27, n] float64.  CUDA tensor in -> CUDA tensor [n, nb, 3] out (asynchronous on
+    the current stream); NumPy array / CPU tensor in -> NumPy array out (copies pipelined in
+    the C library)."""
+    if isinstance(params, torch.Tensor) and params.is_cuda:
+        return default_engine(params.device).forward_bands(params, sensor, out=out, precision=precision)
+    return default_engine(device).forward_bands_host(params, sensor, out=out, precision=precision)
+
+
+def run_batch(leaf, soil, canopy, angles, atm, doy, sensor, precision="fp64", device=None, out=None):
+    """Batched SPART forward run -> [n, nb, 3] ordered (R_TOC, R_TOA, L_TOA)."""
+    return run_batch_params(pack_batch(leaf, soil, canopy, angles, atm, doy, device), sensor, precision, device, out)
+
+
+def row_as_dataframe(out_row, sensor, engine=None):
+    """One row [nb, 3] of a batch result as the DataFrame `SPART.run()` returns
+    (SPART.py:254-260): columns Band, L_TOA, R_TOA, R_TOC indexed by band-centre wavelength."""
+    _, st = (engine or default_engine()).sensor(sensor)
+    r = out_row.detach().cpu().numpy() if isinstance(out_row, torch.Tensor) else np.asarray(out_row)
+    return pd.DataFrame(zip(st.band_id, r[:, 2], r[:, 1], r[:, 0]), index=st.wl_smac,
+                        columns=["Band", "L_TOA", "R_TOA", "R_TOC"])

@@ -1,0 +1,182 @@
+"""Parity of the CUDA path (called through the C ABI) against the oracle and the golden
+fixtures recorded from the unmodified reference.
+
+FP64 gate (BASELINE.json north_star): relative error <= 1e-9 against the reference's
+documented arithmetic (O2 / oracle).  Against the raw reference (O1) the bound is the
+reference's own QUADPACK noise, <= 5e-8 relative and inside the 1.5e-7 absolute tolerance
+of the reference's unit tests."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from conftest import load_golden, relerr  # noqa: E402
+
+RTOL64 = 1e-9
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import spart_b200
+    import spart_oracle as so
+    assert torch.cuda.is_available()
+    return torch, spart_b200, so
+
+
+def gpu_bands(env, P, sensor):
+    torch, sb, _ = env
+    dev = torch.from_numpy(np.ascontiguousarray(np.asarray(P, dtype=np.float64).T)).cuda()
+    out = sb.run_batch_params(dev, sensor)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["cfg2_S2A", "cfg3_L8", "cfg5_S2B", "rand_MODIS", "rand_OLCI", "rand_L7"])
+def test_bands_vs_reference_golden(env, name):
+    g = load_golden(f"batch_{name}.npz")
+    got = gpu_bands(env, g["params"], str(g["sensor"]))
+    assert got.shape == g["O2"].shape
+    assert relerr(got, g["O2"]) < RTOL64
+    assert relerr(got, g["O1"]) < 5e-8
+    assert np.max(np.abs(got[..., :2] - g["O1"][..., :2])) < 1.5e-7
+
+
+@pytest.mark.parametrize("sensor,cfg", [("Sentinel2A-MSI", 2), ("LANDSAT8-OLI", 3), ("TerraAqua-MODIS", 3),
+                                        ("Sentinel3B-OLCI", 3), ("LANDSAT5-TM", 2), ("Sentinel2B-MSI", 5)])
+def test_bands_vs_oracle_random(env, sensor, cfg):
+    _, _, so = env
+    P = so.synthetic_params(2000, cfg, seed=1000 + cfg)
+    want = so.spart_bands(P, sensor)
+    got = gpu_bands(env, P, sensor)
+    assert relerr(got, want) < RTOL64
+
+
+def test_e2e_defaults_all_sensors(env):
+    """The reference's e2e test (tests/e2e/test_SPART.py) through the reference-shaped API."""
+    _, sb, so = env
+    g = load_golden("e2e.npz")
+    for sensor in so.SENSORS:
+        spart = sb.SPART(sb.SoilParameters(0.5, 0, 100, 20, 25, 0.015), sb.LeafBiology(40, 0.01, 0.02, 0, 10, 10, 1.5),
+                         sb.CanopyStructure(3, -0.35, -0.15, 0.05), sb.AtmosphericProperties(0.325, 0.35, 1.41),
+                         sb.Angles(40, 0, 0), sensor, 100)
+        res = spart.run()
+        assert list(res.columns) == ["Band", "L_TOA", "R_TOA", "R_TOC"]
+        assert (res["L_TOA"] > 0).all() and (res["R_TOA"] > 0).all() and (res["R_TOC"] > 0).all()
+        got = np.stack([res["R_TOC"].to_numpy(), res["R_TOA"].to_numpy(), res["L_TOA"].to_numpy()], axis=1)
+        assert relerr(got, g[f"{sensor}.O2"]) < RTOL64
+        assert relerr(got, g[f"{sensor}.O1"]) < 5e-8
+
+
+def test_readme_quickstart(env):
+    _, sb, _ = env
+    g = load_golden("e2e.npz")
+    spart = sb.SPART(sb.SoilParameters(0.5, 0, 100, 15, 25, 0.015), sb.LeafBiology(40, 10, 0.02, 0.01, 0, 10, 1.5),
+                     sb.CanopyStructure(3, -0.35, -0.15, 0.05), sb.AtmosphericProperties(0.3246, 0.3480, 1.4116, 1013.25),
+                     sb.Angles(40, 0, 0), "TerraAqua-MODIS", 100)
+    res = spart.run()
+    got = np.stack([res["R_TOC"].to_numpy(), res["R_TOA"].to_numpy(), res["L_TOA"].to_numpy()], axis=1)
+    assert np.isfinite(got).all()
+    assert relerr(got, g["README.O2"]) < RTOL64
+    assert res.index.to_numpy().tolist() == pytest.approx(sb.load_sensor_info("TerraAqua-MODIS")["wl_smac"].T[0].tolist())
+
+
+def test_spectra_vs_reference_golden(env):
+    torch, sb, so = env
+    g = load_golden("spectra.npz")
+    P = g["params"]
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    spec = sb.default_engine().forward_spectrum(dev).cpu().numpy()
+    names = ["leaf_refl", "leaf_tran", "kChlrel", "soil_refl", "soil_refl_dry", "rso", "rdo", "rsd", "rdd"]
+    for i, k in enumerate(names):
+        ref = g[f"O2.{k}"]
+        got = spec[:, i, :ref.shape[1]]
+        assert (np.isnan(got) == np.isnan(ref)).all(), k
+        assert relerr(got, ref) < RTOL64, k
+        o1 = g[f"O1.{k}"]
+        ok = ~np.isnan(o1)
+        assert np.max(np.abs(got[ok] - o1[ok])) < 1.5e-7, k
+
+
+def test_leafangles(env):
+    _, sb, so = env
+    rng = np.random.default_rng(5)
+    ab = np.stack([rng.uniform(-1, 1, 4000), rng.uniform(-1, 1, 4000)], axis=1)
+    ab = ab[np.abs(ab).sum(1) <= 1.0]
+    ab = np.concatenate([ab, [[-0.35, -0.15], [0.0, 0.0], [1.0, 0.0], [-1.0, 0.0], [0.0, 1.0], [0.0, -1.0]]])
+    want = so.leafangles(ab[:, 0], ab[:, 1])
+    got = sb.default_engine().leafangles(ab)
+    assert np.max(np.abs(got - want)) < 1e-12
+    g = load_golden("sailh_grid.npz")
+    got = sb.default_engine().leafangles(g["canopy_angles7"][:, 1:3])
+    assert np.max(np.abs(got - g["lidf"])) < 1e-12
+
+
+def test_host_path_equals_device_path(env):
+    _, sb, so = env
+    P = so.synthetic_params(5000, 3, seed=9)
+    dev = gpu_bands(env, P, "LANDSAT8-OLI")
+    pt = np.ascontiguousarray(P.T)
+    host = sb.run_batch_params(pt, "LANDSAT8-OLI")
+    assert np.array_equal(host, dev)
+    # strided rows (ld > n): a column window of a larger block
+    big = np.zeros((27, 7000))
+    big[:, 1000:6000] = pt
+    host2 = sb.run_batch_params(big[:, 1000:6000], "LANDSAT8-OLI")
+    assert np.array_equal(host2, dev)
+
+
+def test_edge_cases(env):
+    """Empty and single-sample batches, dry soil branch (bsm.py:102-103), PROSPECT-PRO switch
+    (prospect_5d.py:148-155), exact hot spot dso == 0 (sailh.py:126-127), relative azimuth
+    folding (sailh.py:65) and the SMAC cksi clamp (smac.py:134-135)."""
+    torch, sb, so = env
+    assert gpu_bands(env, np.zeros((0, 27)), "Sentinel2A-MSI").shape == (0, 13, 3)
+    P = so.synthetic_params(64, 3, seed=77)
+    P[0:8, so.SMP] = [0.0, 4.99, 5.0, 5.01, 3.0, 1.0, 5.0, 2.0]          # mu <= 0 -> wet = dry
+    P[8:16, so.CDM] = 0.01                                              # PRO inputs with Cdm > 0
+    P[16:24, so.VZA] = P[16:24, so.SZA]
+    P[16:24, so.RAA] = 0.0                                              # dso == 0
+    P[24:28, so.RAA] = [180.0, 360.0, 540.0, 270.0]
+    P[28:32, so.SZA] = 0.0
+    P[28:32, so.VZA] = 0.0                                              # cksi = -1 (clamp boundary)
+    P[32:36, so.LAI] = [1e-3, 0.01, 10.0, 15.0]
+    for sensor in ("LANDSAT8-OLI", "TerraAqua-MODIS"):
+        want = so.spart_bands(P, sensor)
+        got = gpu_bands(env, P, sensor)
+        assert relerr(got, want) < RTOL64
+    one = gpu_bands(env, P[:1], "LANDSAT8-OLI")
+    assert np.array_equal(one[0], gpu_bands(env, P, "LANDSAT8-OLI")[0])
+
+
+def test_cfg4_synthetic_fullspectrum_sensor(env):
+    _, sb, so = env
+    g = load_golden("batch_cfg4_SYNTH2001.npz")
+    info = sb.synthetic_fullspectrum_sensorinfo()
+    got = gpu_bands(env, g["params"], info)
+    assert got.shape == (g["params"].shape[0], 2001, 3)
+    assert relerr(got, g["O2"]) < RTOL64
+    assert relerr(got, g["O1"]) < 1e-6
+
+
+def test_large_batch_properties(env):
+    """1M-sample configuration of BASELINE.json (config 2): size-independent properties --
+    determinism, independence from batch position, finiteness and physical range."""
+    torch, sb, so = env
+    n = 1_000_000
+    P = so.synthetic_params(n, 2)
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    a = sb.run_batch_params(dev, "Sentinel2A-MSI")
+    b = sb.run_batch_params(dev, "Sentinel2A-MSI")
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    assert torch.isfinite(a).all()
+    assert (a[..., 0] > 0).all() and (a[..., 0] < 1).all() and (a[..., 1] > 0).all() and (a[..., 1] < 1.5).all()
+    # a permuted batch gives the permuted result (no cross-sample state)
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator("cuda").manual_seed(3))
+    c = sb.run_batch_params(dev[:, perm].contiguous(), "Sentinel2A-MSI")
+    assert torch.equal(c, a[perm])
+    # spot-check 256 random rows against the oracle
+    idx = np.random.default_rng(0).choice(n, 256, replace=False)
+    want = so.spart_bands(P[idx], "Sentinel2A-MSI")
+    assert relerr(a[torch.from_numpy(idx).cuda()].cpu().numpy(), want) < RTOL64
