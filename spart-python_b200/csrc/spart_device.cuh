@@ -48,6 +48,7 @@ enum SmacRow {
   SM_REST1, SM_REST2, SM_REST3, SM_REST4,
   SM_RESR1, SM_RESR2, SM_RESR3,
   SM_RESA1, SM_RESA2, SM_RESA3, SM_RESA4,
+  SM_RESR2TAUR,                 // Resr2 * taur: a pure-coefficient product (float32 for Sentinel-2)
   SM_USED,
   SM_COUNT = 60
 };
@@ -458,7 +459,7 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double aer_ref = (aer_ref1 + aer_ref2 + aer_ref3) / usuv;
 
   const double rr = taur * S.ray_phase / usuv;
-  const double Res_ray = c[SM_RESR1] + c[SM_RESR2] * rr + c[SM_RESR3] * (rr * rr);
+  const double Res_ray = c[SM_RESR1] + c[SM_RESR2TAUR] * S.ray_phase / usuv + c[SM_RESR3] * (rr * rr);
   const double ta = taup * m * cksi;
   const double Res_aer = (c[SM_RESA1] + c[SM_RESA2] * ta + c[SM_RESA3] * (ta * ta)) + c[SM_RESA4] * (ta * ta * ta);
   const double tautot = taup + taurz;

@@ -77,7 +77,8 @@ class Engine:
     # ---- device path ---------------------------------------------------------------
     def _prep(self, params):
         if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64
-                and params.dim() == 2 and params.shape[0] == NPAR and params.stride(1) == 1):
+                and params.dim() == 2 and params.shape[0] == NPAR
+                and (params.shape[1] <= 1 or params.stride(1) == 1)):
             raise ValueError("params must be a CUDA float64 tensor [27, n] with contiguous rows")
         if params.device != self.device:
             raise ValueError(f"params on {params.device}, engine on {self.device}")
