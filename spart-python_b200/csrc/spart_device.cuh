@@ -9,6 +9,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "math_coeffs.h"
 #include "tau_coeffs.h"
 
 namespace spart {
@@ -49,6 +50,7 @@ enum SmacRow {
   SM_RESR1, SM_RESR2, SM_RESR3,
   SM_RESA1, SM_RESA2, SM_RESA3, SM_RESA4,
   SM_RESR2TAUR,                 // Resr2 * taur: a pure-coefficient product (float32 for Sentinel-2)
+  SM_AKD3,                      // ak / (3 - wo 3 gc)
   SM_USED,
   SM_COUNT = 60
 };
@@ -64,6 +66,10 @@ enum RecRow {
   R_LO3, R_LH2O, R_LM, R_LPEQ, // ln(uo3 m), ln(uh2o m), ln m, ln Peq
   R_CKSI, R_KSID, R_RAYPH,     // scattering angle terms (smac.py:129-141)
   R_ETSCALE,                   // cf(DOY) cos(sza)/pi (SPART.py:345-353)
+  R_INVUS, R_INVUV,            // 1/us, 1/uv
+  R_INV1PUS, R_INV1PUV,        // 1/(1+us), 1/(1+uv) (smac.py:125-126)
+  R_AA3,                       // us uv / (us + uv) (smac.py:173)
+  R_Z,                         // (1 - tau_ss tau_oo) / (K + k) (sailh.py:203)
   R_COUNT
 };
 
@@ -74,15 +80,39 @@ __constant__ double c_tau_coef[SPART_TAU_NINT][SPART_TAU_DEG + 1];
 __constant__ double c_tau_mid[SPART_TAU_NINT];
 __constant__ double c_tau_invhalf[SPART_TAU_NINT];
 
-// 8-point Gauss-Legendre rule on [-1, 1]
-__constant__ double c_gl8_x[8] = {
-    -0.96028985649753623168, -0.79666647741362673959, -0.52553240991632898582,
-    -0.18343464249564980494, 0.18343464249564980494, 0.52553240991632898582,
-    0.79666647741362673959, 0.96028985649753623168};
-__constant__ double c_gl8_w[8] = {
-    0.10122853629037625915, 0.22238103445337447054, 0.31370664587788728734,
-    0.36268378337836198297, 0.36268378337836198297, 0.31370664587788728734,
-    0.22238103445337447054, 0.10122853629037625915};
+// 12-point Gauss-Legendre rule on [-1, 1] (hot-spot integral)
+#define SPART_NQ 12
+__constant__ double c_gl_x[SPART_NQ] = SPART_GL12_X;
+__constant__ double c_gl_w[SPART_NQ] = SPART_GL12_W;
+
+// ---- bounded-range sine / cosine ------------------------------------------------------------
+// |x| is at most a few pi here (leaf-angle iteration), so a two-term Cody-Waite reduction by
+// pi/2 is exact to the last bit and no large-argument path is needed.  Accuracy ~1 ulp
+// (tools/gen_math_coeffs.py checks the polynomial kernels against 50-digit values).
+__device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
+  const double PS[7] = SPART_SIN_POLY;
+  const double PC[7] = SPART_COS_POLY;
+  // round-to-nearest of x * 2/pi with the 1.5 * 2^52 trick: no F2I / I2F conversions
+  const double magic = 6755399441055744.0;
+  const double t = fma(x, SPART_TWO_OVER_PI, magic);
+  const int q = __double2loint(t);
+  const double qd = t - magic;
+  double r = fma(-qd, SPART_PIO2_HI, x);
+  r = fma(-qd, SPART_PIO2_LO, r);
+  const double z = r * r;
+  double ps = PS[6], pc = PC[6];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    ps = fma(ps, z, PS[i]);
+    pc = fma(pc, z, PC[i]);
+  }
+  const double s0 = fma(r * z, ps, r);
+  const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const double sa = (q & 1) ? c0 : s0;
+  const double ca = (q & 1) ? s0 : c0;
+  sn = (q & 2) ? -sa : sa;
+  cs = ((q + 1) & 2) ? -ca : ca;
+}
 
 // ---- PROSPECT plate transmissivity -----------------------------------------------------
 // tau(K) = (1-K) e^-K + K^2 E1(K)  (prospect_5d.py:182-196).  The reference integrates
@@ -133,8 +163,10 @@ __device__ __forceinline__ double plate_tau(double K, const TauTable* tab) {
 }
 
 // ---- PROSPECT-5D / PROSPECT-PRO at one wavelength (prospect_5d.py:117-246) --------------
+// Divisions that share a denominator are done as one reciprocal and multiplications; this
+// changes individual roundings by <= 1 ulp with respect to the reference's operation order.
 struct LeafPar {
-  double Cab, Cca, Cdm, Cw, Cs, Cant, CBC, PROT, N;
+  double Cab, Cca, Cdm, Cw, Cs, Cant, CBC, PROT, N, invN;
 };
 
 __device__ __forceinline__ LeafPar load_leaf(const double* __restrict__ P, int64_t ld, int64_t s) {
@@ -150,51 +182,57 @@ __device__ __forceinline__ LeafPar load_leaf(const double* __restrict__ P, int64
   L.CBC = P[P_CBC * ld + s];
   // PROSPECT-PRO switch, prospect_5d.py:148-155
   if ((L.PROT > 0.0 || L.CBC > 0.0) && L.Cdm > 0.0) L.Cdm = 0.0;
+  L.invN = 1.0 / L.N;
   return L;
 }
 
 // lc: the SPART_NLC constants of this wavelength.  Returns refl, tran (and kChlrel).
+template <bool kWantKchl>
 __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* lc, const TauTable* tab,
                                                double& refl, double& tran, double& kchl) {
-  const double Kall = (L.Cab * lc[LC_KAB] + L.Cca * lc[LC_KCA] + L.Cdm * lc[LC_KDM] + L.Cw * lc[LC_KW] +
-                       L.Cs * lc[LC_KS] + L.Cant * lc[LC_KANT] + L.CBC * lc[LC_CBC] + L.PROT * lc[LC_PROT]) /
-                      L.N;
+  const double Ksum = L.Cab * lc[LC_KAB] + L.Cca * lc[LC_KCA] + L.Cdm * lc[LC_KDM] + L.Cw * lc[LC_KW] +
+                      L.Cs * lc[LC_KS] + L.Cant * lc[LC_KANT] + L.CBC * lc[LC_CBC] + L.PROT * lc[LC_PROT];
+  const double Kall = Ksum * L.invN;
   double tau = 1.0;
   kchl = 0.0;
   if (Kall > 0.0) {
     tau = plate_tau(Kall, tab);
-    kchl = L.Cab * lc[LC_KAB] / (Kall * L.N);
+    if (kWantKchl) kchl = L.Cab * lc[LC_KAB] / (Kall * L.N);
   }
   const double t_alph = lc[LC_TALPH], t12 = lc[LC_T12], t21 = lc[LC_T21];
   const double r_alph = 1.0 - t_alph, r12 = 1.0 - t12, r21 = 1.0 - t21;
 
   // one plate, prospect_5d.py:208-214
-  double denom = 1.0 - r21 * r21 * tau * tau;
-  const double Ta = t_alph * tau * t21 / denom;
+  const double tt21 = tau * t21;
+  const double inv_d1 = 1.0 / (1.0 - r21 * r21 * tau * tau);
+  const double Ta = t_alph * tt21 * inv_d1;
   const double Ra = r_alph + r21 * tau * Ta;
-  const double t = t12 * tau * t21 / denom;
+  const double t = t12 * tt21 * inv_d1;
   const double r = r12 + r21 * tau * t;
 
   // Stokes system for the remaining N-1 plates, prospect_5d.py:219-230
   double Rsub, Tsub;
+  const double Nm1 = L.N - 1.0;
   if (r + t >= 1.0) {  // zero absorption, prospect_5d.py:233-235
-    Tsub = t / (t + (1.0 - t) * (L.N - 1.0));
+    Tsub = t / (t + (1.0 - t) * Nm1);
     Rsub = 1.0 - Tsub;
   } else {
     const double D = sqrt((1.0 + r + t) * (1.0 + r - t) * (1.0 - r + t) * (1.0 - r - t));
     const double rq = r * r, tq = t * t;
     const double a = (1.0 + rq - tq + D) / (2.0 * r);
     const double b = (1.0 - rq + tq + D) / (2.0 * t);
-    const double bNm1 = pow(b, L.N - 1.0);
+    // b ** (N - 1): b >= 1 and |(N-1) ln b| is O(1), so exp(y ln b) is accurate to a few ulp;
+    // the exact cases of pow are kept (y == 0 -> 1, b == inf -> inf).
+    const double bNm1 = (Nm1 == 0.0) ? 1.0 : exp(Nm1 * log(b));
     const double bN2 = bNm1 * bNm1;
     const double a2 = a * a;
-    denom = a2 * bN2 - 1.0;
-    Rsub = a * (bN2 - 1.0) / denom;
-    Tsub = bNm1 * (a2 - 1.0) / denom;
+    const double inv_d2 = 1.0 / (a2 * bN2 - 1.0);
+    Rsub = a * (bN2 - 1.0) * inv_d2;
+    Tsub = bNm1 * (a2 - 1.0) * inv_d2;
   }
-  denom = 1.0 - Rsub * r;  // prospect_5d.py:239-241
-  tran = Ta * Tsub / denom;
-  refl = Ra + Ta * Rsub * t / denom;
+  const double inv_d3 = 1.0 / (1.0 - Rsub * r);  // prospect_5d.py:239-241
+  tran = Ta * Tsub * inv_d3;
+  refl = Ra + Ta * Rsub * t * inv_d3;
 }
 
 // ---- BSM soil at one wavelength (bsm.py:49-52, 99-124) ----------------------------------
@@ -216,7 +254,7 @@ __device__ __forceinline__ void bsm_point(const SoilPar& S, const double* lc, do
 #pragma unroll
     for (int k = 1; k <= 6; ++k) {
       tw *= tw1;                 // exp(-2 kw film k)
-      fk = fk * S.mu / (double)k;
+      fk = fk * S.mu * (1.0 / (double)k);
       const double x = tw * rbac;
       acc += (Rw + g * x / (1.0 - p * x)) * fk;
     }
@@ -226,7 +264,7 @@ __device__ __forceinline__ void bsm_point(const SoilPar& S, const double* lc, do
 
 // ---- SAILH four-stream solution at one wavelength (sailh.py:99-105, 142-233) ------------
 struct CanopyGeo {
-  double LAI, k, K, bf, sob, sof, tau_ss, tau_oo, sumpso, pso2w;
+  double LAI, k, K, bf, sob, sof, tau_ss, tau_oo, sumpso, pso2w, Z;
 };
 
 __device__ __forceinline__ double sail_J1(double m, double k, double LAI, double em, double ek) {
@@ -258,75 +296,53 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
 
   const double e1 = exp(-m * LAI);
   const double e2 = e1 * e1;
-  const double J1k = sail_J1(m, k, LAI, e1, G.tau_ss);
-  const double J2k = (1.0 - G.tau_ss * e1) / (k + m);   // calcJ2 at x = 0 (sailh.py:172-177)
-  const double J1K = sail_J1(m, K, LAI, e1, G.tau_oo);
-  const double J2K = (1.0 - G.tau_oo * e1) / (K + m);
+  const double tau_ss = G.tau_ss, tau_oo = G.tau_oo;
+  const double inv_km = 1.0 / (k + m), inv_Km = 1.0 / (K + m);
+  const double J1k = sail_J1(m, k, LAI, e1, tau_ss);
+  const double J2k = (1.0 - tau_ss * e1) * inv_km;   // calcJ2 at x = 0 (sailh.py:172-177)
+  const double J1K = sail_J1(m, K, LAI, e1, tau_oo);
+  const double J2K = (1.0 - tau_oo * e1) * inv_Km;
   const double re = rinf * e1;
-  double denom = 1.0 - rinf2 * rinf2;
+  const double inv_den = 1.0 / (1.0 - rinf2 * rinf2);
 
   const double s1 = sf + rinf * sb, s2 = sf * rinf + sb;
   const double v1 = vf + rinf * vb, v2 = vf * rinf + vb;
   const double Pss = s1 * J1k, Qss = s2 * J2k;
   const double Poo = v1 * J1K, Qoo = v2 * J2K;
-  const double tau_ss = G.tau_ss, tau_oo = G.tau_oo;
-  const double Z = (1.0 - tau_ss * tau_oo) / (K + k);
+  const double Z = G.Z;
 
-  const double tau_dd = (1.0 - rinf2) * e1 / denom;
-  const double rho_dd = rinf * (1.0 - e2) / denom;
-  const double tau_sd = (Pss - re * Qss) / denom;
-  const double tau_do = (Poo - re * Qoo) / denom;
-  const double rho_sd = (Qss - re * Pss) / denom;
-  const double rho_do = (Qoo - re * Poo) / denom;
+  const double tau_dd = (1.0 - rinf2) * e1 * inv_den;
+  const double rho_dd = rinf * (1.0 - e2) * inv_den;
+  const double tau_sd = (Pss - re * Qss) * inv_den;
+  const double tau_do = (Poo - re * Qoo) * inv_den;
+  const double rho_sd = (Qss - re * Pss) * inv_den;
+  const double rho_do = (Qoo - re * Poo) * inv_den;
 
-  const double T1 = v2 * s1 * (Z - J1k * tau_oo) / (K + m) + v1 * s2 * (Z - J1K * tau_ss) / (k + m);
+  const double T1 = v2 * s1 * (Z - J1k * tau_oo) * inv_Km + v1 * s2 * (Z - J1K * tau_ss) * inv_km;
   const double T2 = -(Qoo * rho_sd + Poo * tau_sd) * rinf;
   const double rho_sod = (T1 + T2) / (1.0 - rinf2);
   const double rho_so = rho_sod + w * G.sumpso;
 
-  denom = 1.0 - rs * rho_dd;
-  rso = rho_so + rs * G.pso2w +
-        ((tau_sd + tau_ss * rs * rho_dd) * tau_oo + (tau_sd + tau_ss) * tau_do) * rs / denom;
-  rdo = rho_do + (tau_oo + tau_do) * rs * tau_dd / denom;
-  rsd = rho_sd + (tau_ss + tau_sd) * rs * tau_dd / denom;
-  rdd = rho_dd + tau_dd * rs * tau_dd / denom;
+  const double rs_den = rs / (1.0 - rs * rho_dd);
+  rso = rho_so + rs * G.pso2w + ((tau_sd + tau_ss * rs * rho_dd) * tau_oo + (tau_sd + tau_ss) * tau_do) * rs_den;
+  rdo = rho_do + (tau_oo + tau_do) * tau_dd * rs_den;
+  rsd = rho_sd + (tau_ss + tau_sd) * tau_dd * rs_den;
+  rdd = rho_dd + tau_dd * tau_dd * rs_den;
 }
 
 // ---- leaf inclination distribution (sailh.py:351-398) ------------------------------------
-// The reference's dcum is a fixed-point iteration stopped at |dx| <= 1e-8 whose result
-// depends on the number of steps taken, so it is reproduced step for step.  The twelve
-// angles are run through ONE flattened loop so that a warp pays max-over-lanes of the
-// per-sample total instead of the sum over angles of per-angle maxima.
-// F must point at 12 doubles with stride `fs` (shared memory): F[i*fs] = dcum(theta_{i+1}).
-__device__ __forceinline__ void lidf_cumulative(double a, double b, double* F, int fs) {
-  const double rd = SPART_PI / 180.0;
-  if (a > 1.0) {  // sailh.py:371-372
-    for (int i = 0; i < 12; ++i) {
-      const double theta = (i < 8) ? 10.0 * (i + 1) : 80.0 + 2.0 * (i - 7);
-      F[i * fs] = 1.0 - cos(theta * rd);
-    }
-    return;
-  }
-  int i = 0;
-  double theta2 = 2.0 * rd * 10.0;
-  double x = theta2;
-  int guard = 0;
-  while (i < 12) {
-    double s, c;
-    sincos(x, &s, &c);
-    const double y = s * (a + b * c);            // a sin x + 0.5 b sin 2x
-    const double dx = 0.5 * (y - x + theta2);
-    x += dx;
-    if (!(fabs(dx) > 1e-8) || ++guard > 100000) {  // converged (or NaN / runaway input)
-      F[i * fs] = (2.0 * y + theta2) / SPART_PI;
-      ++i;
-      const double theta = (i < 8) ? 10.0 * (i + 1) : 80.0 + 2.0 * (i - 7);
-      theta2 = 2.0 * rd * theta;
-      x = theta2;
-      guard = 0;
-    }
-  }
+// One step of the reference's dcum fixed-point iteration (sailh.py:378-382).  The iteration
+// is stopped at |dx| <= 1e-8 and its result depends on the number of steps taken, so it is
+// reproduced step for step; sin 2x is formed as 2 sin x cos x (<= 1 ulp from the direct value).
+__device__ __forceinline__ bool dcum_step(double a, double b, double theta2, double& x, double& y) {
+  double s, c;
+  sincos_small(x, s, c);
+  y = s * (a + b * c);            // a sin x + 0.5 b sin 2x
+  const double dx = 0.5 * (y - x + theta2);
+  x += dx;
+  return !(fabs(dx) > 1e-8);      // converged (NaN input also stops)
 }
+
 
 // ---- per-class geometry (sailh.py:401-446) ---------------------------------------------
 __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, double sin_tto, double cos_tto,
@@ -353,113 +369,147 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
 }
 
 // ---- hot-spot integrals (sailh.py:116-135, 216-219) --------------------------------------
-// Pso[j] = mean over [xl_j - dx, xl_j] of exp((K+k) LAI x + sqrt(Kk) LAI/alpha (1 - e^{alpha x})).
-// Returns sum_{j<60} Pso[j] * LAI*dx (the bidirectional gap integral) and Pso[60].
-// Each of the 61 panels is integrated with an 8-point Gauss-Legendre rule; the reference's
-// QUADPACK call evaluates a 21-point Kronrod rule on the same panels.
+// pso(x) = exp(A x + Cq (1 - e^{alpha x})),  A = (K+k) LAI,  Cq = sqrt(Kk) LAI / alpha.
+// The reference needs sum_{j<60} Pso[j] * LAI/60 = LAI * int_{-1}^{0} pso dx and
+// Pso[60] = 60 * int_{-1-1/60}^{-1} pso dx, each Pso[j] from one QUADPACK call.
+// Here the first integral is split at x = -L, L = min(1, 40/alpha, 40/(A - sqrt(Kk) LAI)):
+//   * below -L either e^{alpha x} < e^-40 (pso is a pure exponential, integrated in closed
+//     form) or pso itself is < e^-40 of its peak (dropped);
+//   * [-L, 0] is covered by SPART_NP panels of a 12-point Gauss-Legendre rule; on every panel
+//     the exponent varies by at most ~4 and the e^{alpha x} kink by at most e^4, for which
+//     the rule is accurate to ~1e-14 (tools/check notes in DESIGN.md).
+// All lanes run the same trip counts (no divergence); cost 142 exp instead of 557.
+#define SPART_NP 10
 __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI, double q, double dso,
                                                   double& sumpso_ilai, double& pso2w) {
-  const int nl = 60;
-  const double dx = 1.0 / nl;
-  double A = (K + k) * LAI;
-  double Cq = 0.0, alpha = 0.0;
+  const double A0 = (K + k) * LAI;
+  const double S = sqrt(K * k) * LAI;
+  const double Amin = A0 - S;
+  double A = A0, Cq = 0.0, alpha = 0.0;
   if (dso != 0.0) {
     alpha = (dso / q) * 2.0 / (k + K);
-    Cq = sqrt(K * k) * LAI / alpha;
+    Cq = S / alpha;
   } else {
-    A -= sqrt(K * k) * LAI;   // sailh.py:127
+    A = Amin;   // sailh.py:127
   }
-  double gnode[8];
+  double L = 1.0;
+  if (alpha > 0.0) L = fmin(L, 40.0 / alpha);
+  if (Amin > 0.0) L = fmin(L, 40.0 / Amin);
+  const double h = L * (1.0 / SPART_NP);
+  const double ah = alpha * h;
+  double gnode[SPART_NQ];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) gnode[i] = exp(alpha * (0.5 * dx) * c_gl8_x[i]);
-  double total = 0.0, last = 0.0;
-  for (int j = 0; j <= nl; ++j) {
-    const double xc = -(j + 0.5) * dx;          // panel centre
+  for (int i = 0; i < SPART_NQ; ++i) gnode[i] = exp((0.5 * ah) * c_gl_x[i]);
+  double total = 0.0;
+#pragma unroll 1
+  for (int j = 0; j < SPART_NP; ++j) {
+    const double xc = -(j + 0.5) * h;          // panel centre
     const double ej = exp(alpha * xc);
     double acc = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double x = fma(0.5 * dx, c_gl8_x[i], xc);
+    for (int i = 0; i < SPART_NQ; ++i) {
+      const double x = fma(0.5 * h, c_gl_x[i], xc);
       const double arg = fma(A, x, Cq * (1.0 - ej * gnode[i]));
-      acc = fma(c_gl8_w[i], exp(arg), acc);
+      acc = fma(c_gl_w[i], exp(arg), acc);
     }
-    acc *= 0.5;                                  // (dx/2) * sum / dx
-    if (j < nl) total += acc;
-    else last = acc;
+    total += acc;
   }
-  sumpso_ilai = total * (LAI * dx);
-  pso2w = last;
+  total *= 0.5 * h;
+  if (L < 1.0 && alpha * L >= 40.0 * (1.0 - 1e-12)) {  // analytic pure-exponential remainder
+    total += exp(Cq - A * L) * (1.0 - exp(-A * (1.0 - L))) / A;
+  }
+  sumpso_ilai = total * LAI;
+
+  // Pso[60]: mean over [-1 - 1/60, -1] (sailh.py:219)
+  const double dx = 1.0 / 60.0;
+  const double xc = -1.0 - 0.5 * dx;
+  const double ec = exp(alpha * xc);
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < SPART_NQ; ++i) {
+    const double x = fma(0.5 * dx, c_gl_x[i], xc);
+    const double arg = fma(A, x, Cq * (1.0 - ec * exp((0.5 * dx * alpha) * c_gl_x[i])));
+    acc = fma(c_gl_w[i], exp(arg), acc);
+  }
+  pso2w = 0.5 * acc;
 }
 
 // ---- SMAC atmosphere at one band (smac.py:94-207) + TOC->TOA (SPART.py:235-252) ---------
+// u^n is evaluated as exp(n ln u) with the logarithms taken once per sample; gases whose
+// coefficient a is zero for this band contribute exp(0) = 1 and are skipped (warp-uniform
+// branch); exp(-taup/aa_i) are products of exp(-taup/us), exp(-taup/uv), exp(+-ak taup).
 struct AtmSample {
   double us, uv, m, Peq, lo3, lh2o, lm, lpeq, cksi, ksiD, ray_phase, taup550;
+  double inv_us, inv_uv, inv_1pus, inv_1puv, aa3;
 };
 
 __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* c, double conv_ea, double etscale,
                                               double rv_so, double rv_do, double rv_dd, double rv_sd,
                                               double& R_TOC, double& R_TOA, double& L_TOA) {
   const double us = S.us, uv = S.uv, m = S.m, Peq = S.Peq, taup550 = S.taup550;
+  const double inv_us = S.inv_us, inv_uv = S.inv_uv;
   const double taup = c[SM_A0TAUP] + c[SM_A1TAUP] * taup550;
 
-  // gaseous transmission, smac.py:105-119; u^n evaluated as exp(n ln u), product as one exp
-  double gsum = c[SM_AO3] * exp(c[SM_NO3] * S.lo3);
-  gsum += c[SM_AH2O] * exp(c[SM_NH2O] * S.lh2o);
-  gsum += c[SM_AO2] * exp(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
-  gsum += c[SM_ACO2] * exp(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
-  gsum += c[SM_ACH4] * exp(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
-  gsum += c[SM_ANO2] * exp(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
-  gsum += c[SM_ACO] * exp(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
+  // gaseous transmission, smac.py:105-119
+  double gsum = 0.0;
+  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp(c[SM_NO3] * S.lo3);
+  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp(c[SM_NH2O] * S.lh2o);
+  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
+  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
+  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
+  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
+  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
   const double tg = exp(gsum);
 
   const double s = c[SM_A0S] * Peq + c[SM_A3S] + c[SM_A1S] * taup550 + c[SM_A2S] * taup550 * taup550;
   const double tnum = c[SM_A2T] * Peq + c[SM_A3T];
-  const double ttetas = c[SM_A0T] + c[SM_A1T] * taup550 / us + tnum / (1.0 + us);
-  const double ttetav = c[SM_A0T] + c[SM_A1T] * taup550 / uv + tnum / (1.0 + uv);
+  const double ttetas = c[SM_A0T] + c[SM_A1T] * taup550 * inv_us + tnum * S.inv_1pus;
+  const double ttetav = c[SM_A0T] + c[SM_A1T] * taup550 * inv_uv + tnum * S.inv_1puv;
 
   const double cksi = S.cksi, ksiD = S.ksiD;
   const double taur = c[SM_TAUR];
-  const double usuv = us * uv;
-  double ray_ref = (taur * S.ray_phase) / (4.0 * usuv);
-  ray_ref = ray_ref * Peq;      // smac.py:143 (Pa / 1013.25)
+  const double inv_usuv = inv_us * inv_uv;
+  const double rr = taur * S.ray_phase * inv_usuv;
+  const double ray_ref = 0.25 * rr * Peq;    // smac.py:142-143
   const double taurz = taur * Peq;
 
   const double ksi2 = ksiD * ksiD;
   const double aer_phase = c[SM_A0P] + c[SM_A1P] * ksiD + c[SM_A2P] * ksi2 + c[SM_A3P] * (ksi2 * ksiD) +
                            c[SM_A4P] * (ksi2 * ksi2);
   const double wo = c[SM_WO], ak2 = c[SM_AK2], ak = c[SM_AK];
-  const double opb = c[SM_OPB], omb = c[SM_OMB], g3 = c[SM_G3], d3 = c[SM_D3], h3 = c[SM_H3];
+  const double opb = c[SM_OPB], omb = c[SM_OMB], g3 = c[SM_G3], h3 = c[SM_H3], akd3 = c[SM_AKD3];
 
   const double us2 = us * us;
-  const double den4 = 4.0 * (1.0 - ak2 * us2);
-  const double e = -3.0 * us2 * wo / den4;
-  const double f = -h3 * us2 * wo / den4;
-  const double dp = e / (3.0 * us) + us * f;
+  const double inv_q = 1.0 / (1.0 - ak2 * us2);
+  const double e = -0.75 * us2 * wo * inv_q;
+  const double f = -0.25 * h3 * us2 * wo * inv_q;
+  const double dp = e * inv_us * (1.0 / 3.0) + us * f;
   const double d = e + f;
-  const double eak = exp(ak * taup), emak = exp(-ak * taup);
-  const double delta = eak * c[SM_OPB2] - emak * c[SM_OMB2];
-  const double ss = us / (1.0 - ak2 * us2);
+  const double eak = exp(ak * taup);
+  const double emak = 1.0 / eak;
+  const double inv_delta = 1.0 / (eak * c[SM_OPB2] - emak * c[SM_OMB2]);
+  const double ss = us * inv_q;
   const double q1 = 2.0 + 3.0 * us + h3 * us * (1.0 + 2.0 * us);
   const double q2 = 2.0 - 3.0 * us - h3 * us * (1.0 - 2.0 * us);
-  const double q3 = q2 * exp(-taup / us);
-  const double wsd = (c[SM_WW] * ss) / delta;
+  const double Eu = exp(-taup * inv_us), Ev = exp(-taup * inv_uv);
+  const double q3 = q2 * Eu;
+  const double wsd = c[SM_WW] * ss * inv_delta;
   const double c1 = wsd * (q1 * eak * opb + q3 * omb);
   const double c2 = -wsd * (q1 * emak * omb + q3 * opb);
-  const double cp1 = c1 * ak / d3;
-  const double cp2 = -c2 * ak / d3;
-  const double z = d - g3 * uv * dp + wo * aer_phase / 4.0;
-  const double x = c1 - g3 * uv * cp1;
-  const double y = c2 - g3 * uv * cp2;
+  const double cp1 = c1 * akd3;
+  const double cp2 = -c2 * akd3;
+  const double g3uv = g3 * uv;
+  const double z = d - g3uv * dp + wo * aer_phase * 0.25;
+  const double x = c1 - g3uv * cp1;
+  const double y = c2 - g3uv * cp2;
   const double aa1 = uv / (1.0 + ak * uv);
   const double aa2 = uv / (1.0 - ak * uv);
-  const double aa3 = usuv / (us + uv);
-  const double aer_ref1 = x * aa1 * (1.0 - exp(-taup / aa1));
-  const double aer_ref2 = y * aa2 * (1.0 - exp(-taup / aa2));
-  const double aer_ref3 = z * aa3 * (1.0 - exp(-taup / aa3));
-  const double aer_ref = (aer_ref1 + aer_ref2 + aer_ref3) / usuv;
+  const double aer_ref1 = x * aa1 * (1.0 - Ev * emak);   // exp(-taup/aa1) = exp(-taup/uv - ak taup)
+  const double aer_ref2 = y * aa2 * (1.0 - Ev * eak);
+  const double aer_ref3 = z * S.aa3 * (1.0 - Ev * Eu);
+  const double aer_ref = (aer_ref1 + aer_ref2 + aer_ref3) * inv_usuv;
 
-  const double rr = taur * S.ray_phase / usuv;
-  const double Res_ray = c[SM_RESR1] + c[SM_RESR2TAUR] * S.ray_phase / usuv + c[SM_RESR3] * (rr * rr);
+  const double Res_ray = c[SM_RESR1] + c[SM_RESR2TAUR] * S.ray_phase * inv_usuv + c[SM_RESR3] * (rr * rr);
   const double ta = taup * m * cksi;
   const double Res_aer = (c[SM_RESA1] + c[SM_RESA2] * ta + c[SM_RESA3] * (ta * ta)) + c[SM_RESA4] * (ta * ta * ta);
   const double tautot = taup + taurz;
@@ -467,17 +517,17 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double Res_6s = (c[SM_REST1] + c[SM_REST2] * tt + c[SM_REST3] * (tt * tt)) + c[SM_REST4] * (tt * tt * tt);
   const double atm_ref = ray_ref - Res_ray + aer_ref - Res_aer + Res_6s;
 
-  const double ta_ss = exp(-tautot / us);
-  const double ta_oo = exp(-tautot / uv);
+  const double ta_ss = exp(-tautot * inv_us);
+  const double ta_oo = exp(-tautot * inv_uv);
   const double ta_sd = ttetas - ta_ss;
   const double ta_do = ttetav - ta_oo;
 
   // SPART.py:243-252
   const double ra_dd = s, ra_so = atm_ref;
-  const double ms = 1.0 - rv_dd * ra_dd;
+  const double inv_ms = 1.0 / (1.0 - rv_dd * ra_dd);
   const double rtoa0 = ra_so + ta_ss * rv_so * ta_oo;
-  const double rtoa1 = (ta_sd * rv_do + ta_ss * rv_sd * ra_dd * rv_do) * ta_oo / ms;
-  const double rtoa2 = (ta_ss * rv_sd + ta_sd * rv_dd) * ta_do / ms;
+  const double rtoa1 = (ta_sd * rv_do + ta_ss * rv_sd * ra_dd * rv_do) * ta_oo * inv_ms;
+  const double rtoa2 = (ta_ss * rv_sd + ta_sd * rv_dd) * ta_do * inv_ms;
   R_TOC = (ta_ss * rv_so + ta_sd * rv_do) / (ta_ss + ta_sd);
   R_TOA = tg * (rtoa0 + rtoa1 + rtoa2);
   L_TOA = (conv_ea * etscale) * R_TOA;

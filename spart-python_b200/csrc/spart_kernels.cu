@@ -97,16 +97,70 @@ struct SpartCtx {
 // --------------------------------------------------------------------------------------
 constexpr int kSampleThreads = 128;
 
+// Leaf inclination distribution for the 32 samples of a warp (sailh.py:351-398).
+// The 32 x 12 (sample, angle) fixed-point iterations need between 1 and ~120 steps each, so
+// they are treated as a queue of 384 tasks: a lane that converges stores its F value and
+// takes the next task, which keeps all lanes busy until the queue drains.
+// sA/sB: this warp's 32 LIDFa/LIDFb values; sF: [12][kSampleThreads] cumulative values,
+// column = thread index in the block.
+__constant__ double c_theta2[12];   // 2 * (pi/180) * theta for theta = 10..80 step 10, 82..88 step 2
+
+__device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, double* sF, int warp_base) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int ntask = 12 * 32;
+  int next = 32;                 // warp-uniform: first unassigned task
+  int slot = warp_base + lane;   // sF index of the running task: angle * kSampleThreads + column
+  double a = sA[lane], b = sB[lane];
+  double theta2 = c_theta2[0];
+  double x = theta2, y = 0.0;
+  bool active = true;
+  bool force = a > 1.0;          // sailh.py:371-372: closed form, no iteration
+  int guard = 0;
+  while (__any_sync(full, active)) {
+    bool done = false;
+    if (active) done = dcum_step(a, b, theta2, x, y) || force || (++guard > 100000);
+    const unsigned dm = __ballot_sync(full, active && done);
+    if (dm) {
+      if (active && done) {
+        // (2y + theta2)/pi is formed when F is read back; 1 - cos(theta) = 1 - cos(theta2 / 2)
+        sF[slot] = force ? SPART_PI * (1.0 - cos(0.5 * theta2)) : (2.0 * y + theta2);
+        const int task = next + __popc(dm & lt_mask);
+        active = task < ntask;
+        if (active) {            // task t -> angle t / 32, sample t % 32
+          const int ang = task >> 5, smp = task & 31;
+          slot = ang * kSampleThreads + warp_base + smp;
+          a = sA[smp];
+          b = sB[smp];
+          force = a > 1.0;
+          theta2 = c_theta2[ang];
+          x = theta2;
+          guard = 0;
+        }
+      }
+      next += __popc(dm);
+    }
+  }
+  __syncwarp();
+}
+
 // One thread per sample: everything that does not depend on wavelength or band.
 __global__ void __launch_bounds__(kSampleThreads)
 sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec) {
-  __shared__ double sF[12][kSampleThreads];
-  const int64_t s = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
-  if (s >= n) return;
+  __shared__ double sF[12 * kSampleThreads];
+  __shared__ double sA[kSampleThreads], sB[kSampleThreads];
   const int tid = threadIdx.x;
+  const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
+  const bool valid = s_raw < n;
+  const int64_t s = valid ? s_raw : n - 1;     // tail threads shadow the last sample, never store
 
   // leaf inclination distribution (CanopyStructure.__init__, sailh.py:340-398)
-  lidf_cumulative(P[P_LIDFA * ld + s], P[P_LIDFB * ld + s], &sF[0][tid], kSampleThreads);
+  sA[tid] = P[P_LIDFA * ld + s];
+  sB[tid] = P[P_LIDFB * ld + s];
+  __syncwarp();
+  warp_lidf(&sA[tid & ~31], &sB[tid & ~31], sF, tid & ~31);
+  if (!valid) return;
 
   // sun / observer geometry (sailh.py:59-78)
   const double tts = P[P_SZA * ld + s], tto = P[P_VZA * ld + s], rel = P[P_RAA * ld + s];
@@ -122,17 +176,18 @@ sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __res
   // 13 leaf-inclination classes, dotted with lidf (sailh.py:81-97)
   double k = 0.0, K = 0.0, bf = 0.0, sob = 0.0, sof = 0.0;
   const double inv_cc = SPART_PI / (cos_tts * cos_tto);
+  const double inv_cs = 1.0 / cos_tts, inv_co = 1.0 / cos_tto;
   double Fprev = 0.0;
 #pragma unroll 1
   for (int i = 0; i < 13; ++i) {
-    const double Fi = (i < 12) ? sF[i][tid] : 1.0;
+    const double Fi = (i < 12) ? sF[i * kSampleThreads + tid] * (1.0 / SPART_PI) : 1.0;
     const double lidf = Fi - Fprev;
     Fprev = Fi;
     double chi_s, chi_o, frho, ftau;
     volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
                    chi_o, frho, ftau);
-    k += (chi_s / cos_tts) * lidf;
-    K += (chi_o / cos_tto) * lidf;
+    k += (chi_s * inv_cs) * lidf;
+    K += (chi_o * inv_co) * lidf;
     bf += (c_cos_ttli[i] * c_cos_ttli[i]) * lidf;
     sob += (frho * inv_cc) * lidf;
     sof += (ftau * inv_cc) * lidf;
@@ -142,15 +197,17 @@ sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __res
   double sumpso, pso2w;
   hotspot_integrals(K, k, LAI, q, dso, sumpso, pso2w);
 
+  const double tau_ss = exp(-k * LAI), tau_oo = exp(-K * LAI);
   rec[R_K_SUN * n + s] = k;
   rec[R_K_OBS * n + s] = K;
   rec[R_BF * n + s] = bf;
   rec[R_SOB * n + s] = sob;
   rec[R_SOF * n + s] = sof;
-  rec[R_TAUSS * n + s] = exp(-k * LAI);
-  rec[R_TAUOO * n + s] = exp(-K * LAI);
+  rec[R_TAUSS * n + s] = tau_ss;
+  rec[R_TAUOO * n + s] = tau_oo;
   rec[R_SUMPSO * n + s] = sumpso;
   rec[R_PSO2W * n + s] = pso2w;
+  rec[R_Z * n + s] = (1.0 - tau_ss * tau_oo) / (K + k);
 
   // BSM soil-vector weights and Poisson mean (bsm.py:49-51, 101)
   {
@@ -170,7 +227,7 @@ sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __res
   {
     const double us = cos_tts, uv = cos_tto;    // cos(tts*cdr), cos(tto*cdr)
     const double Peq = P[P_PA * ld + s] / 1013.25;
-    const double m = 1.0 / us + 1.0 / uv;
+    const double m = inv_cs + inv_co;
     const double crd = 180.0 / SPART_PI;
     double cksi = -((us * uv) + (sqrt(1.0 - us * us) * sqrt(1.0 - uv * uv) * cos(rel * crd)));
     if (cksi < -1.0) cksi = -1.0;
@@ -186,6 +243,11 @@ sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __res
     rec[R_CKSI * n + s] = cksi;
     rec[R_KSID * n + s] = ksiD;
     rec[R_RAYPH * n + s] = 0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742;
+    rec[R_INVUS * n + s] = inv_cs;
+    rec[R_INVUV * n + s] = inv_co;
+    rec[R_INV1PUS * n + s] = 1.0 / (1.0 + us);
+    rec[R_INV1PUV * n + s] = 1.0 / (1.0 + uv);
+    rec[R_AA3 * n + s] = us * uv / (us + uv);
     // extraterrestrial radiance scale (SPART.py:345-353)
     const double b = 2.0 * SPART_PI * P[P_DOY * ld + s] / 365.0;
     double sb, cb, s2b, c2b;
@@ -209,6 +271,7 @@ __device__ __forceinline__ CanopyGeo load_geo(const double* __restrict__ P, int6
   G.tau_oo = rec[R_TAUOO * n + s];
   G.sumpso = rec[R_SUMPSO * n + s];
   G.pso2w = rec[R_PSO2W * n + s];
+  G.Z = rec[R_Z * n + s];
   return G;
 }
 
@@ -244,23 +307,25 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   const SoilPar S = load_soil(P, ld, rec, n, s);
   const CanopyGeo G = load_geo(P, ld, rec, n, s);
 
-  double rso, rdo, rsd, rdd;
-  {
-    double refl, tran, kchl, rwet, rdry;
-    prospect_point(L, &s_bt[BT_LC0], &s_tau, refl, tran, kchl);
-    bsm_point(S, &s_bt[BT_LC0], rwet, rdry);
-    sailh_point(G, refl, tran, rwet, rso, rdo, rsd, rdd);
-  }
-  if (s_bt[BT_NPTS] > 1.5) {  // band centre between two knots: np.interp (SPART.py:220-223)
-    double refl, tran, kchl, rwet, rdry, rso1, rdo1, rsd1, rdd1;
-    prospect_point(L, &s_bt[BT_LC1], &s_tau, refl, tran, kchl);
-    bsm_point(S, &s_bt[BT_LC1], rwet, rdry);
-    sailh_point(G, refl, tran, rwet, rso1, rdo1, rsd1, rdd1);
-    const double fr = s_bt[BT_FRAC];
-    rso = (rso1 - rso) * fr + rso;
-    rdo = (rdo1 - rdo) * fr + rdo;
-    rsd = (rsd1 - rsd) * fr + rsd;
-    rdd = (rdd1 - rdd) * fr + rdd;
+  // PROSPECT + BSM + SAILH at the one or two wavelengths np.interp touches (SPART.py:220-223)
+  double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
+  const int npts = (s_bt[BT_NPTS] > 1.5) ? 2 : 1;
+#pragma unroll 1
+  for (int pt = 0; pt < npts; ++pt) {
+    const double* lc = &s_bt[BT_LC0 + pt * LC_COUNT];
+    double refl, tran, kchl, rwet, rdry, a0, a1, a2, a3;
+    prospect_point<false>(L, lc, &s_tau, refl, tran, kchl);
+    bsm_point(S, lc, rwet, rdry);
+    sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
+    if (pt == 0) {
+      rso = a0; rdo = a1; rsd = a2; rdd = a3;
+    } else {
+      const double fr = s_bt[BT_FRAC];
+      rso = (a0 - rso) * fr + rso;
+      rdo = (a1 - rdo) * fr + rdo;
+      rsd = (a2 - rsd) * fr + rsd;
+      rdd = (a3 - rdd) * fr + rdd;
+    }
   }
 
   AtmSample A;
@@ -276,6 +341,11 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   A.ksiD = rec[R_KSID * n + s];
   A.ray_phase = rec[R_RAYPH * n + s];
   A.taup550 = P[P_AOT * ld + s];
+  A.inv_us = rec[R_INVUS * n + s];
+  A.inv_uv = rec[R_INVUV * n + s];
+  A.inv_1pus = rec[R_INV1PUS * n + s];
+  A.inv_1puv = rec[R_INV1PUV * n + s];
+  A.aa3 = rec[R_AA3 * n + s];
 
   double R_TOC, R_TOA, L_TOA;
   smac_toa_band(A, &s_bt[BT_SMAC], s_bt[BT_CONVEA], rec[R_ETSCALE * n + s], rso, rdo, rdd, rsd, R_TOC, R_TOA,
@@ -315,7 +385,7 @@ spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
     double refl, tran, kchl, rwet, rdry, rso, rdo, rsd, rdd;
     bsm_point(S, s_lc[j], rwet, rdry);
     if (w < SPART_NWL) {
-      prospect_point(L, s_lc[j], &s_tau, refl, tran, kchl);
+      prospect_point<true>(L, s_lc[j], &s_tau, refl, tran, kchl);
     } else {  // thermal assumptions (SPART.py:461-466; LeafBiology rho/tau_thermal = 0.01)
       refl = 0.01;
       tran = 0.01;
@@ -337,14 +407,20 @@ spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
 // Leaf inclination distribution only (CanopyStructure.lidf, sailh.py:340-398).
 __global__ void __launch_bounds__(kSampleThreads)
 leafangles_kernel(const double* __restrict__ ab, int64_t n, int64_t ld, double* __restrict__ out) {
-  __shared__ double sF[12][kSampleThreads];
-  const int64_t s = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
-  if (s >= n) return;
+  __shared__ double sF[12 * kSampleThreads];
+  __shared__ double sA[kSampleThreads], sB[kSampleThreads];
   const int tid = threadIdx.x;
-  lidf_cumulative(ab[s], ab[ld + s], &sF[0][tid], kSampleThreads);
+  const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
+  const bool valid = s_raw < n;
+  const int64_t s = valid ? s_raw : n - 1;
+  sA[tid] = ab[s];
+  sB[tid] = ab[ld + s];
+  __syncwarp();
+  warp_lidf(&sA[tid & ~31], &sB[tid & ~31], sF, tid & ~31);
+  if (!valid) return;
   double Fprev = 0.0;
   for (int i = 0; i < 13; ++i) {
-    const double Fi = (i < 12) ? sF[i][tid] : 1.0;
+    const double Fi = (i < 12) ? sF[i * kSampleThreads + tid] * (1.0 / SPART_PI) : 1.0;
     out[(size_t)s * 13 + i] = Fi - Fprev;
     Fprev = Fi;
   }
@@ -394,6 +470,36 @@ static int time_fma(int sm_count, double* tflops) {
 // --------------------------------------------------------------------------------------
 // C ABI
 // --------------------------------------------------------------------------------------
+// __constant__ tables are per device: upload them once for every device that is used.
+static int init_device_constants(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) return fail(SPART_EINVAL, "device index out of range%s");
+  if (done[device]) return SPART_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMemcpyToSymbol(c_tau_coef, SPART_TAU_COEF_H, sizeof(SPART_TAU_COEF_H)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_tau_mid, SPART_TAU_MID_H, sizeof(SPART_TAU_MID_H)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_tau_invhalf, SPART_TAU_INVHALF_H, sizeof(SPART_TAU_INVHALF_H)));
+  double sl[13], cl[13];
+  for (int i = 0; i < 13; ++i) {  // litab (sailh.py:49): 5,15,...,75, 81,83,...,89 degrees
+    const double li = (i < 8) ? 5.0 + 10.0 * i : 81.0 + 2.0 * (i - 8);
+    sl[i] = sin(li * (M_PI / 180.0));
+    cl[i] = cos(li * (M_PI / 180.0));
+  }
+  double th2[12];
+  for (int i = 0; i < 12; ++i) {  // dcum angles (sailh.py:388-393) and x0 = 2*rd*theta (sailh.py:376)
+    const double theta = (i < 8) ? 10.0 * (i + 1) : 80.0 + 2.0 * (i - 7);
+    th2[i] = 2.0 * (M_PI / 180.0) * theta;
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(c_theta2, th2, sizeof(th2)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_sin_ttli, sl, sizeof(sl)));
+  CUDA_TRY(cudaMemcpyToSymbol(c_cos_ttli, cl, sizeof(cl)));
+
+  done[device] = true;
+  return SPART_OK;
+}
+
 extern "C" {
 
 int spart_abi_version(void) { return SPART_ABI_VERSION; }
@@ -432,17 +538,13 @@ int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t 
   ctx->n_sensors = n_sensors;
   CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
 
-  CUDA_TRY(cudaMemcpyToSymbol(c_tau_coef, SPART_TAU_COEF_H, sizeof(SPART_TAU_COEF_H)));
-  CUDA_TRY(cudaMemcpyToSymbol(c_tau_mid, SPART_TAU_MID_H, sizeof(SPART_TAU_MID_H)));
-  CUDA_TRY(cudaMemcpyToSymbol(c_tau_invhalf, SPART_TAU_INVHALF_H, sizeof(SPART_TAU_INVHALF_H)));
-  double sl[13], cl[13];
-  for (int i = 0; i < 13; ++i) {  // litab (sailh.py:49): 5,15,...,75, 81,83,...,89 degrees
-    const double li = (i < 8) ? 5.0 + 10.0 * i : 81.0 + 2.0 * (i - 8);
-    sl[i] = sin(li * (M_PI / 180.0));
-    cl[i] = cos(li * (M_PI / 180.0));
+  {
+    int rc = init_device_constants(device);
+    if (rc) {
+      delete ctx;
+      return rc;
+    }
   }
-  CUDA_TRY(cudaMemcpyToSymbol(c_sin_ttli, sl, sizeof(sl)));
-  CUDA_TRY(cudaMemcpyToSymbol(c_cos_ttli, cl, sizeof(cl)));
 
   const size_t lc_bytes = sizeof(double) * LC_COUNT * SPART_NWL;
   CUDA_TRY(cudaMalloc(&ctx->d_lc, lc_bytes));
@@ -603,6 +705,12 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
   if (!ab_dev || !out_dev) return fail(SPART_EINVAL, "spart_leafangles: null argument%s");
   if (n < 0 || ld < n) return fail(SPART_EINVAL, "spart_leafangles: need 0 <= n <= ld%s");
   if (n == 0) return SPART_OK;
+  {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int rc = init_device_constants(dev);
+    if (rc) return rc;
+  }
   const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
   leafangles_kernel<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(ab_dev, n, ld, out_dev);
   ++g_launches;

@@ -42,7 +42,7 @@ SMAC_ROWS = (
     "a0P", "a1P", "a2P", "a3P", "a4P",
     "Rest1", "Rest2", "Rest3", "Rest4", "Resr1", "Resr2", "Resr3",
     "Resa1", "Resa2", "Resa3", "Resa4",
-    "resr2taur",
+    "resr2taur", "akd3",
 )
 
 
@@ -142,6 +142,7 @@ def fold_smac(coef):
         "ak2": ak2, "ak": ak, "opb": 1 + b, "omb": 1 - b, "opb2": (1 + b) ** 2, "omb2": (1 - b) ** 2,
         "ww": wo / 4, "g3": wo * 3 * gc, "d3": 3 - wo * 3 * gc, "h3": (1 - wo) * 3 * gc,
         "resr2taur": c["Resr2"] * c["taur"],          # smac.py:184 evaluates Resr2 * taur first
+        "akd3": f64(ak) / f64(3 - wo * 3 * gc),       # cp1 = c1 * ak / (3 - wo*3*gc), smac.py:166
     }
     # u**n with u = Peq**p * m is evaluated on the device as exp(n*p*ln Peq + n*ln m)
     for gas in ("o2", "co2", "ch4", "no2", "co"):
