@@ -89,16 +89,22 @@ __constant__ double c_gl_w[SPART_NQ] = SPART_GL12_W;
 // |x| is at most a few pi here (leaf-angle iteration), so a two-term Cody-Waite reduction by
 // pi/2 is exact to the last bit and no large-argument path is needed.  Accuracy ~1 ulp
 // (tools/gen_math_coeffs.py checks the polynomial kernels against 50-digit values).
+// Polynomial coefficients live in constant memory so that DFMA reads them as c[bank][offset]
+// operands; as literals the compiler rebuilds each one with two moves on every call.
+__constant__ double c_sin_poly[7] = SPART_SIN_POLY;
+__constant__ double c_cos_poly[7] = SPART_COS_POLY;
+__constant__ double c_trig_red[4] = {SPART_TWO_OVER_PI, 6755399441055744.0, SPART_PIO2_HI, SPART_PIO2_LO};
+
 __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
-  const double PS[7] = SPART_SIN_POLY;
-  const double PC[7] = SPART_COS_POLY;
+  const double* PS = c_sin_poly;
+  const double* PC = c_cos_poly;
   // round-to-nearest of x * 2/pi with the 1.5 * 2^52 trick: no F2I / I2F conversions
-  const double magic = 6755399441055744.0;
-  const double t = fma(x, SPART_TWO_OVER_PI, magic);
+  const double magic = c_trig_red[1];
+  const double t = fma(x, c_trig_red[0], magic);
   const int q = __double2loint(t);
   const double qd = t - magic;
-  double r = fma(-qd, SPART_PIO2_HI, x);
-  r = fma(-qd, SPART_PIO2_LO, r);
+  double r = fma(-qd, c_trig_red[2], x);
+  r = fma(-qd, c_trig_red[3], r);
   const double z = r * r;
   double ps = PS[6], pc = PC[6];
 #pragma unroll
@@ -110,8 +116,9 @@ __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
   const double c0 = fma(z * z, pc, fma(-0.5, z, 1.0));
   const double sa = (q & 1) ? c0 : s0;
   const double ca = (q & 1) ? s0 : c0;
-  sn = (q & 2) ? -sa : sa;
-  cs = ((q + 1) & 2) ? -ca : ca;
+  // quadrant signs applied on the sign bit (integer pipe) instead of FP64 negations
+  sn = __hiloint2double(__double2hiint(sa) ^ ((q & 2) << 30), __double2loint(sa));
+  cs = __hiloint2double(__double2hiint(ca) ^ (((q + 1) & 2) << 30), __double2loint(ca));
 }
 
 // ---- PROSPECT plate transmissivity -----------------------------------------------------
@@ -337,8 +344,8 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
 __device__ __forceinline__ bool dcum_step(double a, double b, double theta2, double& x, double& y) {
   double s, c;
   sincos_small(x, s, c);
-  y = s * (a + b * c);            // a sin x + 0.5 b sin 2x
-  const double dx = 0.5 * (y - x + theta2);
+  y = s * fma(b, c, a);           // a sin x + 0.5 b sin 2x
+  const double dx = fma(0.5, y, 0.5 * (theta2 - x));   // 0.5 (y - x + theta2)
   x += dx;
   return !(fabs(dx) > 1e-8);      // converged (NaN input also stops)
 }

@@ -27,6 +27,17 @@
 
 using namespace spart;
 
+// tuning knobs (tools/tune_variants.sh builds alternatives)
+#ifndef SPART_BAND_CHUNK
+#define SPART_BAND_CHUNK 16
+#endif
+#ifndef SPART_BAND_MINBLOCKS
+#define SPART_BAND_MINBLOCKS 3
+#endif
+#ifndef SPART_SAMPLE_MINBLOCKS
+#define SPART_SAMPLE_MINBLOCKS 5
+#endif
+
 static_assert(LC_COUNT == SPART_NLC, "LC layout");
 static_assert(SM_COUNT == SPART_NSMAC, "SMAC layout");
 static_assert(SM_USED <= SM_COUNT, "SMAC layout");
@@ -146,7 +157,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
 }
 
 // One thread per sample: everything that does not depend on wavelength or band.
-__global__ void __launch_bounds__(kSampleThreads)
+__global__ void __launch_bounds__(kSampleThreads, SPART_SAMPLE_MINBLOCKS)
 sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec) {
   __shared__ double sF[12 * kSampleThreads];
   __shared__ double sA[kSampleThreads], sB[kSampleThreads];
@@ -288,17 +299,22 @@ __device__ __forceinline__ SoilPar load_soil(const double* __restrict__ P, int64
 }
 
 constexpr int kBandThreads = 128;
+constexpr int kBandChunk = SPART_BAND_CHUNK;   // bands handled by one block (per-sample state is loaded once per chunk)
 
-// One thread per (sample, band); blockIdx.x = band (fastest, so the blocks that share a
-// sample tile run together and re-use it from L2), blockIdx.y = sample tile.
-__global__ void __launch_bounds__(kBandThreads)
+// One thread per sample, looping over a chunk of up to kBandChunk bands; blockIdx.x = band
+// chunk, blockIdx.y = sample tile.  The per-sample state (leaf, soil, canopy geometry, SMAC
+// scalars: 44 doubles) is read from HBM once per chunk and kept in registers; the per-band
+// constants are warp-uniform shared-memory broadcasts.
+__global__ void __launch_bounds__(kBandThreads, SPART_BAND_MINBLOCKS)
 band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
             const double* __restrict__ band_table, int nb, double* __restrict__ out) {
   __shared__ TauTable s_tau;
-  __shared__ double s_bt[BT_COUNT];
-  const int b = blockIdx.x;
+  __shared__ double s_bt[kBandChunk][BT_COUNT];
+  const int b0 = blockIdx.x * kBandChunk;
+  const int nbc = min(kBandChunk, nb - b0);
   load_tau_table(&s_tau);
-  for (int i = threadIdx.x; i < BT_COUNT; i += blockDim.x) s_bt[i] = band_table[(size_t)b * BT_COUNT + i];
+  for (int i = threadIdx.x; i < nbc * BT_COUNT; i += blockDim.x)
+    (&s_bt[0][0])[i] = band_table[(size_t)b0 * BT_COUNT + i];
   __syncthreads();
   const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
   if (s >= n) return;
@@ -306,28 +322,6 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   const LeafPar L = load_leaf(P, ld, s);
   const SoilPar S = load_soil(P, ld, rec, n, s);
   const CanopyGeo G = load_geo(P, ld, rec, n, s);
-
-  // PROSPECT + BSM + SAILH at the one or two wavelengths np.interp touches (SPART.py:220-223)
-  double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
-  const int npts = (s_bt[BT_NPTS] > 1.5) ? 2 : 1;
-#pragma unroll 1
-  for (int pt = 0; pt < npts; ++pt) {
-    const double* lc = &s_bt[BT_LC0 + pt * LC_COUNT];
-    double refl, tran, kchl, rwet, rdry, a0, a1, a2, a3;
-    prospect_point<false>(L, lc, &s_tau, refl, tran, kchl);
-    bsm_point(S, lc, rwet, rdry);
-    sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
-    if (pt == 0) {
-      rso = a0; rdo = a1; rsd = a2; rdd = a3;
-    } else {
-      const double fr = s_bt[BT_FRAC];
-      rso = (a0 - rso) * fr + rso;
-      rdo = (a1 - rdo) * fr + rdo;
-      rsd = (a2 - rsd) * fr + rsd;
-      rdd = (a3 - rdd) * fr + rdd;
-    }
-  }
-
   AtmSample A;
   A.us = rec[R_US * n + s];
   A.uv = rec[R_UV * n + s];
@@ -346,14 +340,38 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   A.inv_1pus = rec[R_INV1PUS * n + s];
   A.inv_1puv = rec[R_INV1PUV * n + s];
   A.aa3 = rec[R_AA3 * n + s];
+  const double etscale = rec[R_ETSCALE * n + s];
+  double* o = out + ((size_t)s * nb + b0) * SPART_NOUT;
 
-  double R_TOC, R_TOA, L_TOA;
-  smac_toa_band(A, &s_bt[BT_SMAC], s_bt[BT_CONVEA], rec[R_ETSCALE * n + s], rso, rdo, rdd, rsd, R_TOC, R_TOA,
-                L_TOA);
-  double* o = out + ((size_t)s * nb + b) * SPART_NOUT;
-  o[0] = R_TOC;
-  o[1] = R_TOA;
-  o[2] = L_TOA;
+#pragma unroll 1
+  for (int bi = 0; bi < nbc; ++bi) {
+    const double* bt = s_bt[bi];
+    // PROSPECT + BSM + SAILH at the one or two wavelengths np.interp touches (SPART.py:220-223)
+    double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
+    const int npts = (bt[BT_NPTS] > 1.5) ? 2 : 1;
+#pragma unroll 1
+    for (int pt = 0; pt < npts; ++pt) {
+      const double* lc = &bt[BT_LC0 + pt * LC_COUNT];
+      double refl, tran, kchl, rwet, rdry, a0, a1, a2, a3;
+      prospect_point<false>(L, lc, &s_tau, refl, tran, kchl);
+      bsm_point(S, lc, rwet, rdry);
+      sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
+      if (pt == 0) {
+        rso = a0; rdo = a1; rsd = a2; rdd = a3;
+      } else {
+        const double fr = bt[BT_FRAC];
+        rso = (a0 - rso) * fr + rso;
+        rdo = (a1 - rdo) * fr + rdo;
+        rsd = (a2 - rsd) * fr + rsd;
+        rdd = (a3 - rdd) * fr + rdd;
+      }
+    }
+    double R_TOC, R_TOA, L_TOA;
+    smac_toa_band(A, &bt[BT_SMAC], bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
+    o[bi * SPART_NOUT + 0] = R_TOC;
+    o[bi * SPART_NOUT + 1] = R_TOA;
+    o[bi * SPART_NOUT + 2] = L_TOA;
+  }
 }
 
 // Full-spectrum planes: blockIdx.x = chunk of kSpecChunk wavelengths, blockIdx.y = sample tile.
@@ -644,7 +662,7 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
   if (rc) return rc;
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
   const int nb = ctx->n_bands[sensor];
-  dim3 grid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
+  dim3 grid((unsigned)((nb + kBandChunk - 1) / kBandChunk), (unsigned)((n + kBandThreads - 1) / kBandThreads));
   band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());

@@ -8,7 +8,10 @@ import ctypes
 from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int32, c_int64, c_size_t, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libspart_b200.so"
+import os
+
+# SPART_B200_LIB lets kernel-tuning scripts load an alternative build of the same library
+LIB_PATH = Path(os.environ.get("SPART_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libspart_b200.so")
 ABI_VERSION = 1
 
 FP64 = 64
