@@ -40,10 +40,12 @@ WORKLOAD = "configs[1]: 1M-sample PROSPECT-5D+SAILH LUT, Sentinel2A-MSI (13 band
 # Algorithmic FP64 work per simulation of this workload, in flop (FMA = 2), counted from the
 # executed SASS of each kernel (ncu smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on,
 # profiles/r01_*; see DESIGN.md "Roofline").  Updated whenever a kernel changes.
-FLOP_PER_SAMPLE = {"sample_kernel": 0.0, "band_kernel": 0.0}
-# Algorithmic HBM bytes per simulation: 27 params in (216 B) + 26-double record out and in
-# again (2 x 208 B) + 9 leaf/film/LAI/aot rows re-read by the band kernel + 13 x 3 results.
-BYTES_PER_SAMPLE = {"sample_kernel": 14 * 8 + 26 * 8, "band_kernel": (26 + 12) * 8 + 13 * 3 * 8}
+FLOP_PER_SAMPLE = {"lidf_kernel": 0.0, "geometry_kernel": 0.0, "band_kernel": 0.0}
+# Algorithmic HBM bytes per simulation and kernel: leaf angles read 2 parameter rows and write
+# 12 cumulative values; geometry reads those 12 + 12 parameter rows and writes the 32-double
+# record; the band kernel reads the record + 12 parameter rows and writes 13 x 3 results.
+BYTES_PER_SAMPLE = {"lidf_kernel": (2 + 12) * 8, "geometry_kernel": (12 + 12 + 32) * 8,
+                    "band_kernel": (32 + 12) * 8 + 13 * 3 * 8}
 
 
 def load_flop_counts():
@@ -205,7 +207,7 @@ def run_ours(args):
 
     # --- resident-input timing -------------------------------------------------------
     for _ in range(args.warmup):
-        eng.forward_bands(params, SENSOR, out=out)
+        eng.forward_bands(params, SENSOR, out=out, uniform_geometry=True)
     barrier()
     eng.profile_enable(SENSOR, True)
     sampler = ClockSampler(local)
@@ -215,7 +217,7 @@ def run_ours(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        eng.forward_bands(params, SENSOR, out=out)
+        eng.forward_bands(params, SENSOR, out=out, uniform_geometry=True)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -232,11 +234,11 @@ def run_ours(args):
     host_out = torch.empty((n, nb, 3), dtype=torch.float64).pin_memory()
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(2):
-        spart_b200.run_batch_params(host_in, SENSOR, out=host_out)
+        spart_b200.run_batch_params(host_in, SENSOR, out=host_out, uniform_geometry=True)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        spart_b200.run_batch_params(host_in, SENSOR, out=host_out)
+        spart_b200.run_batch_params(host_in, SENSOR, out=host_out, uniform_geometry=True)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n * e2e_steps / e2e_s
@@ -250,7 +252,8 @@ def run_ours(args):
     # --- roofline of the dominant kernel ----------------------------------------------
     peaks = eng.measure_peaks()
     calls = max(prof["calls"], 1)
-    kern_ms = {"sample_kernel": prof["sample_ms"] / calls, "band_kernel": prof["band_ms"] / calls}
+    kern_ms = {"lidf_kernel": prof["lidf_ms"] / calls, "geometry_kernel": prof["geometry_ms"] / calls,
+               "band_kernel": prof["band_ms"] / calls}
     dominant = max(kern_ms, key=kern_ms.get)
     mp_file = ROOT / "MEASURED_PEAKS.json"
     hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -288,10 +291,10 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "samples_per_gpu_per_step": n, "sensor": SENSOR, "bands": nb,
-                   "l2": "working set per step (216 MB params + 208 MB record + 312 MB output) exceeds the 126 MB L2"},
+                   "l2": "working set per step (216 MB params + 352 MB workspace + 312 MB output) exceeds the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": 27 * 8 * n,
                 "d2h_bytes_per_step": nb * 3 * 8 * n, "steps": e2e_steps,
-                "api": "spart_b200.run_batch_params(pinned host [27,n]) -> pinned host [n,13,3]"},
+                "api": "spart_b200.run_batch_params(pinned host [27,n], uniform_geometry=True) -> pinned host [n,13,3]"},
         "gpu_launches": launches,
         "clocks": sampler.summary(),
         "roofline": roofline, "roofline_hbm": roofline_hbm,

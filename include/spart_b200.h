@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SPART_ABI_VERSION 1
+#define SPART_ABI_VERSION 2
 
 #define SPART_NPAR 27       /* rows of a parameter batch                                   */
 #define SPART_NWL 2001      /* 400..2400 nm, 1 nm (SpectralBands.wlP, SPART.py:303)        */
@@ -49,6 +49,7 @@ extern "C" {
 #define SPART_NSMAC 60      /* per-band host-folded SMAC constants, see SpartSensor        */
 #define SPART_NOUT 3        /* R_TOC, R_TOA, L_TOA                                         */
 #define SPART_NSPEC 9       /* planes of spart_forward_spectrum                            */
+#define SPART_NKERNELS 3    /* kernels of spart_forward_bands: leaf angles, geometry, bands */
 
 enum {
   SPART_OK = 0,
@@ -58,6 +59,14 @@ enum {
 };
 
 enum { SPART_FP64 = 64, SPART_FP32 = 32 };
+
+/* flags of spart_forward_bands */
+enum {
+  /* the caller guarantees that rows 19..21 (sun / observer angles) are constant over the batch,
+   * as in a look-up table for one acquisition geometry; the sample-independent volume-scattering
+   * terms (_volscatt, sailh.py:401-446) are then evaluated once per thread block */
+  SPART_FLAG_UNIFORM_GEOMETRY = 1
+};
 
 typedef struct SpartCtx SpartCtx;
 
@@ -108,8 +117,8 @@ size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n);
  * SPART_FP32 (arithmetic type of the spectral/atmosphere stage; I/O is always double).
  * Asynchronous on `stream`. */
 int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* params_dev,
-                        int64_t n, int64_t ld, int32_t precision, void* workspace_dev,
-                        double* out_dev, void* stream);
+                        int64_t n, int64_t ld, int32_t precision, int32_t flags,
+                        void* workspace_dev, double* out_dev, void* stream);
 
 /* Same computation with HOST buffers: params_host [SPART_NPAR][ld] and out_host
  * [n][n_bands][3] are ordinary (pageable or pinned) host memory; the call stages them
@@ -117,7 +126,8 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
  * streams, and returns when out_host is complete.  This is the drop-in for a caller that
  * holds NumPy arrays. */
 int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params_host,
-                             int64_t n, int64_t ld, int32_t precision, double* out_host);
+                             int64_t n, int64_t ld, int32_t precision, int32_t flags,
+                             double* out_host);
 
 /* Replaces the leafopt / soilopt / canopyopt attributes of a SPART object after run()
  * (SPART.py:192-214, 427-470): full 2162-wavelength spectra.
@@ -134,11 +144,12 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
 
 /* Per-kernel timing of spart_forward_bands with CUDA events recorded on the caller's stream
  * (used by bench.py for the roofline).  After spart_profile_enable(ctx, 1) every
- * spart_forward_bands call records three events around its two kernels; spart_profile_read
- * waits for them and returns the summed durations [ms] of the per-sample kernel and of the
- * per-(sample, band) kernel over `*calls` calls, then clears the list. */
+ * spart_forward_bands call records events around its SPART_NKERNELS kernels; spart_profile_read
+ * waits for them and returns in kernel_ms[0..2] the summed durations [ms] of the leaf-angle
+ * kernel, the per-sample geometry kernel and the per-(sample, band) kernel over `*calls` calls,
+ * then clears the list. */
 int spart_profile_enable(SpartCtx* ctx, int32_t on);
-int spart_profile_read(SpartCtx* ctx, double* sample_ms, double* band_ms, int64_t* calls);
+int spart_profile_read(SpartCtx* ctx, double* kernel_ms, int64_t* calls);
 
 /* Micro-benchmarks used as roofline denominators by bench.py: dependent-free DFMA / FFMA
  * chains on all SMs.  Results in TFLOP/s (FMA = 2 flop). */

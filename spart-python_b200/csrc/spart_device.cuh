@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 #include "math_coeffs.h"
@@ -121,6 +122,95 @@ __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
   cs = __hiloint2double(__double2hiint(ca) ^ (((q + 1) & 2) << 30), __double2loint(ca));
 }
 
+// ---- exp / log with constant-bank coefficients ----------------------------------------------
+// libdevice's exp/log rebuild each of their ~13 polynomial coefficients with two move
+// instructions per call (46 / ~100 SASS instructions per call, 15 / ~25 of them FP64).  These
+// versions read the coefficients as c[bank][offset] operands of the DFMAs: 19 / ~32
+// instructions, same <= 1 ulp accuracy class (tools/gen_math_coeffs.py).  Arguments outside
+// the plain range are handled branch-free with NaN-preserving selects (see each function).
+__constant__ double c_exp_poly[12] = SPART_EXP_POLY;
+__constant__ double c_log_poly[9] = SPART_LOG_POLY;
+__constant__ double c_explog_red[4] = {SPART_LOG2E, 6755399441055744.0, SPART_LN2_HI, SPART_LN2_LO};
+
+
+#ifndef SPART_FAST_EXP
+#define SPART_FAST_EXP 1
+#endif
+#ifndef SPART_FAST_LOG
+#define SPART_FAST_LOG 1
+#endif
+
+// e^r * 2^k core shared by both variants: returns the polynomial value p ~ e^r and k.
+__device__ __forceinline__ double exp_core(double x, int& k) {
+  const double magic = c_explog_red[1];
+  const double t = fma(x, c_explog_red[0], magic);
+  k = __double2loint(t);
+  const double kd = t - magic;
+  double r = fma(-kd, c_explog_red[2], x);
+  r = fma(-kd, c_explog_red[3], r);
+  double p = c_exp_poly[11];
+#pragma unroll
+  for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
+  return p;
+}
+
+// Full-range exp, branch free: the argument is clamped to [-745.2, 709.8] with NaN-preserving
+// selects (exp(-inf) = 0, exp(+inf) = inf, denormal results rounded correctly by the two-step
+// scaling, NaN in -> NaN out).
+__device__ __forceinline__ double exp_fast(double x) {
+#if !SPART_FAST_EXP
+  return exp(x);
+#endif
+  double xc = x;
+  xc = (x < -745.2) ? -745.2 : xc;
+  xc = (x > 709.8) ? 709.8 : xc;
+  int k;
+  const double p = exp_core(xc, k);
+  const int k1 = k >> 1, k2 = k - k1;
+  const double s1 = __hiloint2double((k1 + 1023) << 20, 0);
+  const double s2 = __hiloint2double((k2 + 1023) << 20, 0);
+  return (p * s1) * s2;
+}
+
+// exp for call sites that guarantee |x| <= 700 for finite inputs (NaN still propagates).
+__device__ __forceinline__ double exp_bounded(double x) {
+#if !SPART_FAST_EXP
+  return exp(x);
+#endif
+  int k;
+  const double p = exp_core(x, k);
+  return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
+__device__ __forceinline__ double log_fast(double x) {
+#if !SPART_FAST_LOG
+  return log(x);
+#endif
+  const int hi = __double2hiint(x);
+  int e = (hi >> 20) - 1023;
+  int mh = (hi & 0x000fffff) | 0x3ff00000;
+  if (mh >= 0x3ff6a09f) {        // mantissa above sqrt(2): halve it so that m is in [0.707, 1.414)
+    mh -= 0x00100000;
+    e += 1;
+  }
+  const double m = __hiloint2double(mh, __double2loint(x));
+  const double s = (m - 1.0) / (m + 1.0);
+  const double z = s * s;
+  double p = c_log_poly[8];
+#pragma unroll
+  for (int i = 7; i >= 0; --i) p = fma(p, z, c_log_poly[i]);
+  const double s2 = s + s;
+  const double l = fma(s2 * z, p, s2);     // 2 atanh(s) = ln m
+  // int -> double without I2F: 2^52 + 2^31 + e, minus the bias
+  const double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 4503601774854144.0;
+  const double res = fma(ed, c_explog_red[2], fma(ed, c_explog_red[3], l));
+  // special arguments, branch free: +inf / NaN -> x + x, 0 -> -inf, negative -> NaN
+  // (positive subnormals are not supported: they return x + x)
+  const bool plain = (unsigned)(hi - 0x00100000) < 0x7fe00000u;
+  const double special = (x == 0.0) ? -CUDART_INF : ((x < 0.0) ? CUDART_NAN : x + x);
+  return plain ? res : special;
+}
+
 // ---- PROSPECT plate transmissivity -----------------------------------------------------
 // tau(K) = (1-K) e^-K + K^2 E1(K)  (prospect_5d.py:182-196).  The reference integrates
 // e^-t/t numerically per wavelength; here E1 comes from piecewise polynomials generated in
@@ -147,7 +237,7 @@ __device__ __forceinline__ void load_tau_table(TauTable* s) {
 
 __device__ __forceinline__ double plate_tau(double K, const TauTable* tab) {
   // caller guarantees K > 0
-  const double emk = exp(-K);
+  const double emk = exp_fast(-K);
   int idx;
   double u, t = 1.0 / K;
   if (K < 1.0) {
@@ -163,7 +253,7 @@ __device__ __forceinline__ double plate_tau(double K, const TauTable* tab) {
 #pragma unroll
   for (int i = SPART_TAU_DEG - 1; i >= 0; --i) p = fma(p, u, c[i]);
   if (K < 1.0) {
-    const double e1 = fma(K, p, -0.57721566490153286061 - log(K));
+    const double e1 = fma(K, p, -0.57721566490153286061 - log_fast(K));
     return (1.0 - K) * emk + K * K * e1;
   }
   return emk * t * p;
@@ -228,9 +318,9 @@ __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* l
     const double rq = r * r, tq = t * t;
     const double a = (1.0 + rq - tq + D) / (2.0 * r);
     const double b = (1.0 - rq + tq + D) / (2.0 * t);
-    // b ** (N - 1): b >= 1 and |(N-1) ln b| is O(1), so exp(y ln b) is accurate to a few ulp;
+    // b ** (N - 1): b >= 1 and |(N-1) ln b| is O(1), so exp_fast(y ln b) is accurate to a few ulp;
     // the exact cases of pow are kept (y == 0 -> 1, b == inf -> inf).
-    const double bNm1 = (Nm1 == 0.0) ? 1.0 : exp(Nm1 * log(b));
+    const double bNm1 = (Nm1 == 0.0) ? 1.0 : exp_fast(Nm1 * log_fast(b));
     const double bN2 = bNm1 * bNm1;
     const double a2 = a * a;
     const double inv_d2 = 1.0 / (a2 * bN2 - 1.0);
@@ -253,14 +343,14 @@ __device__ __forceinline__ void bsm_point(const SoilPar& S, const double* lc, do
   if (S.mu > 0.0) {
     const double rbac = 1.0 - (1.0 - rdry) * (rdry * lc[LC_SOILC1] + 1.0 - rdry);
     const double p = lc[LC_SOILP], Rw = lc[LC_SOILRW];
-    const double tw1 = exp(-2.0 * lc[LC_KW] * S.film);
+    const double tw1 = exp_fast(-2.0 * lc[LC_KW] * S.film);
     double fk = S.emu;           // Poisson weight k = 0
     double acc = rdry * fk;
     double tw = 1.0;
     const double g = (1.0 - Rw) * (1.0 - p);
 #pragma unroll
     for (int k = 1; k <= 6; ++k) {
-      tw *= tw1;                 // exp(-2 kw film k)
+      tw *= tw1;                 // exp_fast(-2 kw film k)
       fk = fk * S.mu * (1.0 / (double)k);
       const double x = tw * rbac;
       acc += (Rw + g * x / (1.0 - p * x)) * fk;
@@ -275,7 +365,7 @@ struct CanopyGeo {
 };
 
 __device__ __forceinline__ double sail_J1(double m, double k, double LAI, double em, double ek) {
-  // calcJ1 at x = -1 (sailh.py:154-170); em = exp(-m LAI), ek = exp(-k LAI)
+  // calcJ1 at x = -1 (sailh.py:154-170); em = exp_fast(-m LAI), ek = exp_fast(-k LAI)
   if (fabs((m - k) * LAI) < 1e-6) {
     return 0.5 * (em + ek) * LAI * (1.0 - (1.0 / 12.0) * (k - m) * (k - m) * LAI * LAI);
   }
@@ -301,7 +391,7 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
   const double rinf = (a - m) / sigb;
   const double rinf2 = rinf * rinf;
 
-  const double e1 = exp(-m * LAI);
+  const double e1 = exp_fast(-m * LAI);
   const double e2 = e1 * e1;
   const double tau_ss = G.tau_ss, tau_oo = G.tau_oo;
   const double inv_km = 1.0 / (k + m), inv_Km = 1.0 / (K + m);
@@ -376,7 +466,7 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
 }
 
 // ---- hot-spot integrals (sailh.py:116-135, 216-219) --------------------------------------
-// pso(x) = exp(A x + Cq (1 - e^{alpha x})),  A = (K+k) LAI,  Cq = sqrt(Kk) LAI / alpha.
+// pso(x) = exp_fast(A x + Cq (1 - e^{alpha x})),  A = (K+k) LAI,  Cq = sqrt(Kk) LAI / alpha.
 // The reference needs sum_{j<60} Pso[j] * LAI/60 = LAI * int_{-1}^{0} pso dx and
 // Pso[60] = 60 * int_{-1-1/60}^{-1} pso dx, each Pso[j] from one QUADPACK call.
 // Here the first integral is split at x = -L, L = min(1, 40/alpha, 40/(A - sqrt(Kk) LAI)):
@@ -406,45 +496,45 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
   const double ah = alpha * h;
   double gnode[SPART_NQ];
 #pragma unroll
-  for (int i = 0; i < SPART_NQ; ++i) gnode[i] = exp((0.5 * ah) * c_gl_x[i]);
+  for (int i = 0; i < SPART_NQ; ++i) gnode[i] = exp_bounded((0.5 * ah) * c_gl_x[i]);   // |arg| <= 2
   double total = 0.0;
 #pragma unroll 1
   for (int j = 0; j < SPART_NP; ++j) {
     const double xc = -(j + 0.5) * h;          // panel centre
-    const double ej = exp(alpha * xc);
+    const double ej = exp_bounded(alpha * xc);            // arg in [-40, 0]
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < SPART_NQ; ++i) {
       const double x = fma(0.5 * h, c_gl_x[i], xc);
       const double arg = fma(A, x, Cq * (1.0 - ej * gnode[i]));
-      acc = fma(c_gl_w[i], exp(arg), acc);
+      acc = fma(c_gl_w[i], exp_bounded(arg), acc);       // arg in [-80, 0]: A L <= 40 A / Amin <= 80
     }
     total += acc;
   }
   total *= 0.5 * h;
   if (L < 1.0 && alpha * L >= 40.0 * (1.0 - 1e-12)) {  // analytic pure-exponential remainder
-    total += exp(Cq - A * L) * (1.0 - exp(-A * (1.0 - L))) / A;
+    total += exp_fast(Cq - A * L) * (1.0 - exp_fast(-A * (1.0 - L))) / A;
   }
   sumpso_ilai = total * LAI;
 
   // Pso[60]: mean over [-1 - 1/60, -1] (sailh.py:219)
   const double dx = 1.0 / 60.0;
   const double xc = -1.0 - 0.5 * dx;
-  const double ec = exp(alpha * xc);
+  const double ec = exp_fast(alpha * xc);
   double acc = 0.0;
 #pragma unroll
   for (int i = 0; i < SPART_NQ; ++i) {
     const double x = fma(0.5 * dx, c_gl_x[i], xc);
-    const double arg = fma(A, x, Cq * (1.0 - ec * exp((0.5 * dx * alpha) * c_gl_x[i])));
-    acc = fma(c_gl_w[i], exp(arg), acc);
+    const double arg = fma(A, x, Cq * (1.0 - ec * exp_fast((0.5 * dx * alpha) * c_gl_x[i])));
+    acc = fma(c_gl_w[i], exp_fast(arg), acc);
   }
   pso2w = 0.5 * acc;
 }
 
 // ---- SMAC atmosphere at one band (smac.py:94-207) + TOC->TOA (SPART.py:235-252) ---------
-// u^n is evaluated as exp(n ln u) with the logarithms taken once per sample; gases whose
-// coefficient a is zero for this band contribute exp(0) = 1 and are skipped (warp-uniform
-// branch); exp(-taup/aa_i) are products of exp(-taup/us), exp(-taup/uv), exp(+-ak taup).
+// u^n is evaluated as exp_fast(n ln u) with the logarithms taken once per sample; gases whose
+// coefficient a is zero for this band contribute exp_fast(0) = 1 and are skipped (warp-uniform
+// branch); exp_fast(-taup/aa_i) are products of exp_fast(-taup/us), exp_fast(-taup/uv), exp_fast(+-ak taup).
 struct AtmSample {
   double us, uv, m, Peq, lo3, lh2o, lm, lpeq, cksi, ksiD, ray_phase, taup550;
   double inv_us, inv_uv, inv_1pus, inv_1puv, aa3;
@@ -459,14 +549,14 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
 
   // gaseous transmission, smac.py:105-119
   double gsum = 0.0;
-  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp(c[SM_NO3] * S.lo3);
-  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp(c[SM_NH2O] * S.lh2o);
-  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
-  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
-  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
-  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
-  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
-  const double tg = exp(gsum);
+  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp_fast(c[SM_NO3] * S.lo3);
+  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp_fast(c[SM_NH2O] * S.lh2o);
+  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp_fast(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
+  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp_fast(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
+  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp_fast(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
+  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp_fast(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
+  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp_fast(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
+  const double tg = exp_fast(gsum);
 
   const double s = c[SM_A0S] * Peq + c[SM_A3S] + c[SM_A1S] * taup550 + c[SM_A2S] * taup550 * taup550;
   const double tnum = c[SM_A2T] * Peq + c[SM_A3T];
@@ -492,13 +582,13 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double f = -0.25 * h3 * us2 * wo * inv_q;
   const double dp = e * inv_us * (1.0 / 3.0) + us * f;
   const double d = e + f;
-  const double eak = exp(ak * taup);
+  const double eak = exp_fast(ak * taup);
   const double emak = 1.0 / eak;
   const double inv_delta = 1.0 / (eak * c[SM_OPB2] - emak * c[SM_OMB2]);
   const double ss = us * inv_q;
   const double q1 = 2.0 + 3.0 * us + h3 * us * (1.0 + 2.0 * us);
   const double q2 = 2.0 - 3.0 * us - h3 * us * (1.0 - 2.0 * us);
-  const double Eu = exp(-taup * inv_us), Ev = exp(-taup * inv_uv);
+  const double Eu = exp_fast(-taup * inv_us), Ev = exp_fast(-taup * inv_uv);
   const double q3 = q2 * Eu;
   const double wsd = c[SM_WW] * ss * inv_delta;
   const double c1 = wsd * (q1 * eak * opb + q3 * omb);
@@ -511,7 +601,7 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double y = c2 - g3uv * cp2;
   const double aa1 = uv / (1.0 + ak * uv);
   const double aa2 = uv / (1.0 - ak * uv);
-  const double aer_ref1 = x * aa1 * (1.0 - Ev * emak);   // exp(-taup/aa1) = exp(-taup/uv - ak taup)
+  const double aer_ref1 = x * aa1 * (1.0 - Ev * emak);   // exp_fast(-taup/aa1) = exp_fast(-taup/uv - ak taup)
   const double aer_ref2 = y * aa2 * (1.0 - Ev * eak);
   const double aer_ref3 = z * S.aa3 * (1.0 - Ev * Eu);
   const double aer_ref = (aer_ref1 + aer_ref2 + aer_ref3) * inv_usuv;
@@ -524,8 +614,8 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double Res_6s = (c[SM_REST1] + c[SM_REST2] * tt + c[SM_REST3] * (tt * tt)) + c[SM_REST4] * (tt * tt * tt);
   const double atm_ref = ray_ref - Res_ray + aer_ref - Res_aer + Res_6s;
 
-  const double ta_ss = exp(-tautot * inv_us);
-  const double ta_oo = exp(-tautot * inv_uv);
+  const double ta_ss = exp_fast(-tautot * inv_us);
+  const double ta_oo = exp_fast(-tautot * inv_uv);
   const double ta_sd = ttetas - ta_ss;
   const double ta_do = ttetav - ta_oo;
 

@@ -98,7 +98,7 @@ struct SpartCtx {
   // optional per-kernel timing of spart_forward_bands (spart_profile_enable / _read)
   mutable std::mutex prof_mu;
   mutable bool profiling = false;
-  struct ProfEvents { cudaEvent_t e[3]; };
+  struct ProfEvents { cudaEvent_t e[4]; };
   mutable std::vector<ProfEvents> prof_pending;
   mutable std::vector<ProfEvents> prof_free;
 };
@@ -116,62 +116,108 @@ constexpr int kSampleThreads = 128;
 // column = thread index in the block.
 __constant__ double c_theta2[12];   // 2 * (pi/180) * theta for theta = 10..80 step 10, 82..88 step 2
 
-__device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, double* sF, int warp_base) {
+#ifndef SPART_LIDF_SPW
+#define SPART_LIDF_SPW 64       // samples per warp in the leaf-angle task queue
+#endif
+#ifndef SPART_LIDF_BATCH
+#define SPART_LIDF_BATCH 6      // idle lanes that trigger a (divergent) task hand-out
+#endif
+constexpr int kLidfSpw = SPART_LIDF_SPW;
+
+// Leaf inclination distribution for the kLidfSpw samples of a warp (sailh.py:351-398).
+// The (sample, angle) fixed-point iterations need between 1 and ~120 steps each, so they are
+// treated as a queue of 12 * kLidfSpw tasks: a lane that converges stores its result and goes
+// idle; as soon as SPART_LIDF_BATCH lanes are idle they all receive new tasks in one
+// warp-uniform hand-out (handing out per converged lane would execute the divergent
+// hand-out code on almost every step).  sA/sB: the warp's LIDFa/LIDFb values; sF: the
+// warp's [12][kLidfSpw] results, holding 2 y + theta2 (divided by pi on read-out).
+__device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, double* sF) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int ntask = 12 * 32;
-  int next = 32;                 // warp-uniform: first unassigned task
-  int slot = warp_base + lane;   // sF index of the running task: angle * kSampleThreads + column
+  const int ntask = 12 * kLidfSpw;
+  int next = 32;                 // warp-uniform: first unassigned task; task t -> angle t / SPW, sample t % SPW
+  int slot = lane;               // sF index of the running task
   double a = sA[lane], b = sB[lane];
   double theta2 = c_theta2[0];
   double x = theta2, y = 0.0;
-  bool active = true;
+  bool running = true;
   bool force = a > 1.0;          // sailh.py:371-372: closed form, no iteration
   int guard = 0;
-  while (__any_sync(full, active)) {
-    bool done = false;
-    if (active) done = dcum_step(a, b, theta2, x, y) || force || (++guard > 100000);
-    const unsigned dm = __ballot_sync(full, active && done);
-    if (dm) {
-      if (active && done) {
-        // (2y + theta2)/pi is formed when F is read back; 1 - cos(theta) = 1 - cos(theta2 / 2)
+  while (true) {
+    if (running) {
+      const bool done = dcum_step(a, b, theta2, x, y) || force || (++guard > 100000);
+      if (done) {
         sF[slot] = force ? SPART_PI * (1.0 - cos(0.5 * theta2)) : (2.0 * y + theta2);
-        const int task = next + __popc(dm & lt_mask);
-        active = task < ntask;
-        if (active) {            // task t -> angle t / 32, sample t % 32
-          const int ang = task >> 5, smp = task & 31;
-          slot = ang * kSampleThreads + warp_base + smp;
-          a = sA[smp];
-          b = sB[smp];
-          force = a > 1.0;
-          theta2 = c_theta2[ang];
-          x = theta2;
-          guard = 0;
-        }
+        running = false;
       }
-      next += __popc(dm);
+    }
+    const unsigned idle = __ballot_sync(full, !running);
+    const int nidle = __popc(idle);
+    if (next < ntask) {
+      if (nidle >= SPART_LIDF_BATCH) {
+        if (!running) {
+          const int task = next + __popc(idle & lt_mask);
+          if (task < ntask) {
+            const int ang = task / kLidfSpw, smp = task % kLidfSpw;
+            slot = ang * kLidfSpw + smp;
+            a = sA[smp];
+            b = sB[smp];
+            force = a > 1.0;
+            theta2 = c_theta2[ang];
+            x = theta2;
+            guard = 0;
+            running = true;
+          }
+        }
+        next += nidle;
+      }
+    } else if (nidle == 32) {
+      break;
     }
   }
   __syncwarp();
 }
 
-// One thread per sample: everything that does not depend on wavelength or band.
+// workspace rows: the per-sample record followed by the 12 cumulative leaf-angle values
+constexpr int kRowF = R_COUNT;
+constexpr int kWsRows = R_COUNT + 12;
+
+// Kernel 1: leaf inclination distribution (CanopyStructure.__init__, sailh.py:340-398).
+// A kernel of its own so that it runs at ~40 registers / 64 warps per SM: the iteration is
+// one long dependent FP64 chain per lane and needs the occupancy to fill the FP64 pipe.
+__global__ void __launch_bounds__(kSampleThreads)
+lidf_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ ws) {
+  constexpr int kWarps = kSampleThreads / 32;
+  __shared__ double sF[kWarps][12 * kLidfSpw];
+  __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * kLidfSpw;   // first sample of this warp
+  if (base >= n) return;
+  for (int j = lane; j < kLidfSpw; j += 32) {
+    const int64_t s = (base + j < n) ? base + j : n - 1;     // tail entries shadow the last sample
+    sA[warp][j] = P[P_LIDFA * ld + s];
+    sB[warp][j] = P[P_LIDFB * ld + s];
+  }
+  __syncwarp();
+  warp_lidf(sA[warp], sB[warp], sF[warp]);
+  for (int i = 0; i < 12; ++i)
+    for (int j = lane; j < kLidfSpw; j += 32)
+      if (base + j < n) ws[(size_t)(kRowF + i) * n + base + j] = sF[warp][i * kLidfSpw + j] * (1.0 / SPART_PI);
+}
+
+// Kernel 2, one thread per sample: everything else that does not depend on wavelength or
+// band.  With uniform_geometry != 0 all samples share sun/observer angles (a look-up table
+// for one acquisition geometry): the 13-class volume-scattering terms are then evaluated
+// once per block by 13 threads instead of once per sample.
 __global__ void __launch_bounds__(kSampleThreads, SPART_SAMPLE_MINBLOCKS)
-sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec) {
-  __shared__ double sF[12 * kSampleThreads];
-  __shared__ double sA[kSampleThreads], sB[kSampleThreads];
+geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec,
+                int uniform_geometry) {
+  __shared__ double s_cls[13][4];   // ksli, koli, sobli, sofli per leaf-inclination class
   const int tid = threadIdx.x;
   const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
   const bool valid = s_raw < n;
-  const int64_t s = valid ? s_raw : n - 1;     // tail threads shadow the last sample, never store
-
-  // leaf inclination distribution (CanopyStructure.__init__, sailh.py:340-398)
-  sA[tid] = P[P_LIDFA * ld + s];
-  sB[tid] = P[P_LIDFB * ld + s];
-  __syncwarp();
-  warp_lidf(&sA[tid & ~31], &sB[tid & ~31], sF, tid & ~31);
-  if (!valid) return;
+  const int64_t s = valid ? s_raw : n - 1;
 
   // sun / observer geometry (sailh.py:59-78)
   const double tts = P[P_SZA * ld + s], tto = P[P_VZA * ld + s], rel = P[P_RAA * ld + s];
@@ -183,32 +229,52 @@ sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __res
   const double tan_tts = tan(tts * SPART_DEG2RAD), tan_tto = tan(tto * SPART_DEG2RAD);
   const double cos_psi = cos(psi_rad);
   const double dso = sqrt(tan_tts * tan_tts + tan_tto * tan_tto - 2.0 * tan_tts * tan_tto * cos_psi);
+  const double inv_cc = SPART_PI / (cos_tts * cos_tto);
+  const double inv_cs = 1.0 / cos_tts, inv_co = 1.0 / cos_tto;
+
+  if (uniform_geometry) {
+    if (tid < 13) {
+      double chi_s, chi_o, frho, ftau;
+      volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[tid], c_cos_ttli[tid], chi_s,
+                     chi_o, frho, ftau);
+      s_cls[tid][0] = chi_s * inv_cs;
+      s_cls[tid][1] = chi_o * inv_co;
+      s_cls[tid][2] = frho * inv_cc;
+      s_cls[tid][3] = ftau * inv_cc;
+    }
+    __syncthreads();
+  }
+  if (!valid) return;
 
   // 13 leaf-inclination classes, dotted with lidf (sailh.py:81-97)
   double k = 0.0, K = 0.0, bf = 0.0, sob = 0.0, sof = 0.0;
-  const double inv_cc = SPART_PI / (cos_tts * cos_tto);
-  const double inv_cs = 1.0 / cos_tts, inv_co = 1.0 / cos_tto;
   double Fprev = 0.0;
 #pragma unroll 1
   for (int i = 0; i < 13; ++i) {
-    const double Fi = (i < 12) ? sF[i * kSampleThreads + tid] * (1.0 / SPART_PI) : 1.0;
+    const double Fi = (i < 12) ? rec[(size_t)(kRowF + i) * n + s] : 1.0;
     const double lidf = Fi - Fprev;
     Fprev = Fi;
-    double chi_s, chi_o, frho, ftau;
-    volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
-                   chi_o, frho, ftau);
-    k += (chi_s * inv_cs) * lidf;
-    K += (chi_o * inv_co) * lidf;
+    double ksli, koli, sobli, sofli;
+    if (uniform_geometry) {
+      ksli = s_cls[i][0]; koli = s_cls[i][1]; sobli = s_cls[i][2]; sofli = s_cls[i][3];
+    } else {
+      double chi_s, chi_o, frho, ftau;
+      volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
+                     chi_o, frho, ftau);
+      ksli = chi_s * inv_cs; koli = chi_o * inv_co; sobli = frho * inv_cc; sofli = ftau * inv_cc;
+    }
+    k += ksli * lidf;
+    K += koli * lidf;
     bf += (c_cos_ttli[i] * c_cos_ttli[i]) * lidf;
-    sob += (frho * inv_cc) * lidf;
-    sof += (ftau * inv_cc) * lidf;
+    sob += sobli * lidf;
+    sof += sofli * lidf;
   }
 
   const double LAI = P[P_LAI * ld + s], q = P[P_Q * ld + s];
   double sumpso, pso2w;
   hotspot_integrals(K, k, LAI, q, dso, sumpso, pso2w);
 
-  const double tau_ss = exp(-k * LAI), tau_oo = exp(-K * LAI);
+  const double tau_ss = exp_fast(-k * LAI), tau_oo = exp_fast(-K * LAI);
   rec[R_K_SUN * n + s] = k;
   rec[R_K_OBS * n + s] = K;
   rec[R_BF * n + s] = bf;
@@ -231,7 +297,7 @@ sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __res
     rec[R_F3 * n + s] = B * clat * clon;
     const double mu = (P[P_SMP * ld + s] - 5.0) / P[P_SMC * ld + s];
     rec[R_MU * n + s] = mu;
-    rec[R_EMU * n + s] = exp(-mu);
+    rec[R_EMU * n + s] = exp_fast(-mu);
   }
 
   // SMAC per-sample scalars (smac.py:98-102, 129-141)
@@ -247,10 +313,10 @@ sample_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __res
     rec[R_UV * n + s] = uv;
     rec[R_M * n + s] = m;
     rec[R_PEQ * n + s] = Peq;
-    rec[R_LO3 * n + s] = log(P[P_UO3 * ld + s] * m);
-    rec[R_LH2O * n + s] = log(P[P_UH2O * ld + s] * m);
-    rec[R_LM * n + s] = log(m);
-    rec[R_LPEQ * n + s] = log(Peq);
+    rec[R_LO3 * n + s] = log_fast(P[P_UO3 * ld + s] * m);
+    rec[R_LH2O * n + s] = log_fast(P[P_UH2O * ld + s] * m);
+    rec[R_LM * n + s] = log_fast(m);
+    rec[R_LPEQ * n + s] = log_fast(Peq);
     rec[R_CKSI * n + s] = cksi;
     rec[R_KSID * n + s] = ksiD;
     rec[R_RAYPH * n + s] = 0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742;
@@ -425,22 +491,27 @@ spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
 // Leaf inclination distribution only (CanopyStructure.lidf, sailh.py:340-398).
 __global__ void __launch_bounds__(kSampleThreads)
 leafangles_kernel(const double* __restrict__ ab, int64_t n, int64_t ld, double* __restrict__ out) {
-  __shared__ double sF[12 * kSampleThreads];
-  __shared__ double sA[kSampleThreads], sB[kSampleThreads];
-  const int tid = threadIdx.x;
-  const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
-  const bool valid = s_raw < n;
-  const int64_t s = valid ? s_raw : n - 1;
-  sA[tid] = ab[s];
-  sB[tid] = ab[ld + s];
+  constexpr int kWarps = kSampleThreads / 32;
+  __shared__ double sF[kWarps][12 * kLidfSpw];
+  __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * kLidfSpw;
+  if (base >= n) return;
+  for (int j = lane; j < kLidfSpw; j += 32) {
+    const int64_t s = (base + j < n) ? base + j : n - 1;
+    sA[warp][j] = ab[s];
+    sB[warp][j] = ab[ld + s];
+  }
   __syncwarp();
-  warp_lidf(&sA[tid & ~31], &sB[tid & ~31], sF, tid & ~31);
-  if (!valid) return;
-  double Fprev = 0.0;
-  for (int i = 0; i < 13; ++i) {
-    const double Fi = (i < 12) ? sF[i * kSampleThreads + tid] * (1.0 / SPART_PI) : 1.0;
-    out[(size_t)s * 13 + i] = Fi - Fprev;
-    Fprev = Fi;
+  warp_lidf(sA[warp], sB[warp], sF[warp]);
+  for (int j = lane; j < kLidfSpw; j += 32) {
+    if (base + j >= n) continue;
+    double Fprev = 0.0;
+    for (int i = 0; i < 13; ++i) {
+      const double Fi = (i < 12) ? sF[warp][i * kLidfSpw + j] * (1.0 / SPART_PI) : 1.0;
+      out[(size_t)(base + j) * 13 + i] = Fi - Fprev;
+      Fprev = Fi;
+    }
   }
 }
 
@@ -602,8 +673,8 @@ int spart_destroy(SpartCtx* ctx) {
     if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
   }
-  for (auto& pe : ctx->prof_pending) for (int i = 0; i < 3; ++i) cudaEventDestroy(pe.e[i]);
-  for (auto& pe : ctx->prof_free) for (int i = 0; i < 3; ++i) cudaEventDestroy(pe.e[i]);
+  for (auto& pe : ctx->prof_pending) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
+  for (auto& pe : ctx->prof_free) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
   for (double* d : ctx->d_band) cudaFree(d);
   if (ctx->d_lc) cudaFree(ctx->d_lc);
   delete ctx;
@@ -613,12 +684,22 @@ int spart_destroy(SpartCtx* ctx) {
 size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n) {
   (void)ctx;
   if (n < 0) return 0;
-  return sizeof(double) * (size_t)R_COUNT * (size_t)n;
+  return sizeof(double) * (size_t)kWsRows * (size_t)n;
 }
 
-static int launch_sample(const double* params_dev, int64_t n, int64_t ld, double* rec, cudaStream_t st) {
+static int launch_lidf(const double* params_dev, int64_t n, int64_t ld, double* ws, cudaStream_t st) {
+  const int64_t per_block = (int64_t)(kSampleThreads / 32) * kLidfSpw;
+  const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
+  lidf_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, ws);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return SPART_OK;
+}
+
+static int launch_geometry(const double* params_dev, int64_t n, int64_t ld, double* ws, int uniform,
+                           cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
-  sample_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, rec);
+  geometry_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, ws, uniform);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
@@ -634,7 +715,7 @@ static int check_batch(const SpartCtx* ctx, const void* params, int64_t n, int64
 }
 
 int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* params_dev, int64_t n, int64_t ld,
-                        int32_t precision, void* workspace_dev, double* out_dev, void* stream) {
+                        int32_t precision, int32_t flags, void* workspace_dev, double* out_dev, void* stream) {
   int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_forward_bands");
   if (rc) return rc;
   if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "spart_forward_bands: unknown sensor%s");
@@ -653,21 +734,24 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
         pe = ctx->prof_free.back();
         ctx->prof_free.pop_back();
       } else {
-        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&pe.e[i]));
+        for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&pe.e[i]));
       }
     }
   }
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
-  rc = launch_sample(params_dev, n, ld, rec, st);
+  rc = launch_lidf(params_dev, n, ld, rec, st);
   if (rc) return rc;
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
+  rc = launch_geometry(params_dev, n, ld, rec, (flags & SPART_FLAG_UNIFORM_GEOMETRY) ? 1 : 0, st);
+  if (rc) return rc;
+  if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
   const int nb = ctx->n_bands[sensor];
   dim3 grid((unsigned)((nb + kBandChunk - 1) / kBandChunk), (unsigned)((n + kBandThreads - 1) / kBandThreads));
   band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   if (prof) {
-    CUDA_TRY(cudaEventRecord(pe.e[2], st));
+    CUDA_TRY(cudaEventRecord(pe.e[3], st));
     std::lock_guard<std::mutex> lock(ctx->prof_mu);
     ctx->prof_pending.push_back(pe);
   }
@@ -683,21 +767,20 @@ int spart_profile_enable(SpartCtx* ctx, int32_t on) {
   return SPART_OK;
 }
 
-int spart_profile_read(SpartCtx* ctx, double* sample_ms, double* band_ms, int64_t* calls) {
-  if (!ctx || !sample_ms || !band_ms || !calls) return fail(SPART_EINVAL, "spart_profile_read: null argument%s");
+int spart_profile_read(SpartCtx* ctx, double* kernel_ms, int64_t* calls) {
+  if (!ctx || !kernel_ms || !calls) return fail(SPART_EINVAL, "spart_profile_read: null argument%s");
   std::lock_guard<std::mutex> lock(ctx->prof_mu);
-  double a = 0.0, b = 0.0;
+  double acc[SPART_NKERNELS] = {0.0, 0.0, 0.0};
   for (auto& pe : ctx->prof_pending) {
-    CUDA_TRY(cudaEventSynchronize(pe.e[2]));
-    float m0 = 0.f, m1 = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&m0, pe.e[0], pe.e[1]));
-    CUDA_TRY(cudaEventElapsedTime(&m1, pe.e[1], pe.e[2]));
-    a += m0;
-    b += m1;
+    CUDA_TRY(cudaEventSynchronize(pe.e[3]));
+    for (int k = 0; k < SPART_NKERNELS; ++k) {
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, pe.e[k], pe.e[k + 1]));
+      acc[k] += ms;
+    }
     ctx->prof_free.push_back(pe);
   }
-  *sample_ms = a;
-  *band_ms = b;
+  for (int k = 0; k < SPART_NKERNELS; ++k) kernel_ms[k] = acc[k];
   *calls = (int64_t)ctx->prof_pending.size();
   ctx->prof_pending.clear();
   return SPART_OK;
@@ -710,7 +793,9 @@ int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_
   if (n == 0) return SPART_OK;
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
-  rc = launch_sample(params_dev, n, ld, rec, st);
+  rc = launch_lidf(params_dev, n, ld, rec, st);
+  if (rc) return rc;
+  rc = launch_geometry(params_dev, n, ld, rec, 0, st);
   if (rc) return rc;
   dim3 grid((SPART_NWL_S + kSpecChunk - 1) / kSpecChunk, (unsigned)((n + kSpecThreads - 1) / kSpecThreads));
   spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, out_dev);
@@ -729,7 +814,8 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
     int rc = init_device_constants(dev);
     if (rc) return rc;
   }
-  const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+  const int64_t per_block = (int64_t)(kSampleThreads / 32) * kLidfSpw;
+  const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
   leafangles_kernel<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(ab_dev, n, ld, out_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -747,7 +833,7 @@ static int ensure_slots(SpartCtx* ctx, int64_t chunk, int nb) {
       if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
       ctx->slot_params[i] = ctx->slot_rec[i] = nullptr;
       CUDA_TRY(cudaMalloc(&ctx->slot_params[i], sizeof(double) * P_COUNT * chunk));
-      CUDA_TRY(cudaMalloc(&ctx->slot_rec[i], sizeof(double) * R_COUNT * chunk));
+      CUDA_TRY(cudaMalloc(&ctx->slot_rec[i], sizeof(double) * kWsRows * chunk));
     }
     if (ctx->slot_out_cap < out_need) {
       if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
@@ -761,7 +847,7 @@ static int ensure_slots(SpartCtx* ctx, int64_t chunk, int nb) {
 }
 
 int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params_host, int64_t n, int64_t ld,
-                             int32_t precision, double* out_host) {
+                             int32_t precision, int32_t flags, double* out_host) {
   if (!ctx || !params_host || !out_host) return fail(SPART_EINVAL, "spart_forward_bands_host: null argument%s");
   if (n < 0 || ld < n) return fail(SPART_EINVAL, "spart_forward_bands_host: need 0 <= n <= ld%s");
   if (sensor < 0 || sensor >= ctx->n_sensors)
@@ -786,7 +872,7 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params
     // rows of the SoA batch are ld apart on the host and m apart in the slot
     CUDA_TRY(cudaMemcpy2DAsync(ctx->slot_params[slot], sizeof(double) * m, params_host + s0, sizeof(double) * ld,
                                sizeof(double) * m, P_COUNT, cudaMemcpyHostToDevice, st));
-    rc = spart_forward_bands(ctx, sensor, ctx->slot_params[slot], m, m, precision, ctx->slot_rec[slot],
+    rc = spart_forward_bands(ctx, sensor, ctx->slot_params[slot], m, m, precision, flags, ctx->slot_rec[slot],
                              ctx->slot_out[slot], st);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)s0 * nb * SPART_NOUT, ctx->slot_out[slot],

@@ -12,7 +12,9 @@ import os
 
 # SPART_B200_LIB lets kernel-tuning scripts load an alternative build of the same library
 LIB_PATH = Path(os.environ.get("SPART_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libspart_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_UNIFORM_GEOMETRY = 1
+NKERNELS = 3
 
 FP64 = 64
 FP32 = 32
@@ -63,13 +65,14 @@ def load():
     lib.spart_destroy.argtypes = [c_void_p]
     lib.spart_workspace_bytes.argtypes = [c_void_p, c_int64]
     lib.spart_workspace_bytes.restype = c_size_t
-    lib.spart_forward_bands.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p,
+    lib.spart_forward_bands.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                         c_void_p, c_void_p]
-    lib.spart_forward_bands_host.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_void_p]
+    lib.spart_forward_bands_host.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32,
+                                             c_void_p]
     lib.spart_forward_spectrum.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]
-    lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_int64)]
+    lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]
     lib.spart_measure_peaks.argtypes = [c_int32, POINTER(c_double), POINTER(c_double)]
     lib.spart_launch_count.restype = c_int64
     if lib.spart_abi_version() != ABI_VERSION:

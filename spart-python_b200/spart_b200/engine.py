@@ -84,9 +84,10 @@ class Engine:
             raise ValueError(f"params on {params.device}, engine on {self.device}")
         return params, params.shape[1], (params.stride(0) if params.shape[1] > 1 else max(params.shape[1], 1))
 
-    def forward_bands(self, params, sensor, out=None, precision="fp64"):
+    def forward_bands(self, params, sensor, out=None, precision="fp64", uniform_geometry=False):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
-        Asynchronous on the current torch stream."""
+        Asynchronous on the current torch stream.  uniform_geometry=True asserts that the three
+        angle rows are constant over the batch (SPART_FLAG_UNIFORM_GEOMETRY)."""
         handle, st = self.sensor(sensor)
         params, n, ld = self._prep(params)
         if out is None:
@@ -96,10 +97,11 @@ class Engine:
             raise ValueError("out must be a contiguous CUDA float64 tensor [n, nb, 3]")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         prec = _PRECISION[precision]
+        flags = _lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0
         for s0 in range(0, n, MAX_SAMPLES_PER_CALL):
             m = min(MAX_SAMPLES_PER_CALL, n - s0)
             ws = torch.empty(self.lib.spart_workspace_bytes(handle, m) // 8, dtype=torch.float64, device=self.device)
-            _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr() + 8 * s0, m, ld, prec,
+            _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr() + 8 * s0, m, ld, prec, flags,
                                                     ws.data_ptr(), out.data_ptr() + 8 * s0 * st.n_bands * NOUT,
                                                     stream), "spart_forward_bands")
         return out
@@ -128,7 +130,7 @@ class Engine:
         return out.cpu().numpy()
 
     # ---- host path -----------------------------------------------------------------
-    def forward_bands_host(self, params, sensor, out=None, precision="fp64"):
+    def forward_bands_host(self, params, sensor, out=None, precision="fp64", uniform_geometry=False):
         """params: host float64 [27, n] (NumPy array or CPU tensor, ideally pinned) ->
         host float64 [n, nb, 3].  H2D, kernels and D2H are pipelined inside the C library."""
         handle, st = self.sensor(sensor)
@@ -143,8 +145,9 @@ class Engine:
         if o.dtype != np.float64 or not o.flags.c_contiguous or o.shape != (n, st.n_bands, NOUT):
             raise ValueError("out must be a C-contiguous host float64 array [n, nb, 3]")
         with torch.cuda.device(self.device):
+            flags = _lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0
             _lib.check(self.lib.spart_forward_bands_host(handle, 0, p.ctypes.data, n, ld, _PRECISION[precision],
-                                                         o.ctypes.data), "spart_forward_bands_host")
+                                                         flags, o.ctypes.data), "spart_forward_bands_host")
         return out
 
     def profile_enable(self, sensor, on=True):
@@ -153,12 +156,12 @@ class Engine:
 
     def profile_read(self, sensor):
         """Summed CUDA-event durations of the two kernels since the last read:
-        {'sample_ms', 'band_ms', 'calls'}."""
+        {'lidf_ms', 'geometry_ms', 'band_ms', 'calls'}."""
         handle, _ = self.sensor(sensor)
-        a, b, c = _lib.c_double(), _lib.c_double(), _lib.c_int64()
-        _lib.check(self.lib.spart_profile_read(handle, _lib.byref(a), _lib.byref(b), _lib.byref(c)),
-                   "spart_profile_read")
-        return {"sample_ms": a.value, "band_ms": b.value, "calls": c.value}
+        ms = (_lib.c_double * _lib.NKERNELS)()
+        c = _lib.c_int64()
+        _lib.check(self.lib.spart_profile_read(handle, ms, _lib.byref(c)), "spart_profile_read")
+        return {"lidf_ms": ms[0], "geometry_ms": ms[1], "band_ms": ms[2], "calls": c.value}
 
     def measure_peaks(self):
         a, b = _lib.c_double(), _lib.c_double()

@@ -149,6 +149,21 @@ def test_edge_cases(env):
     assert np.array_equal(one[0], gpu_bands(env, P, "LANDSAT8-OLI")[0])
 
 
+def test_uniform_geometry_flag_is_only_an_optimisation(env):
+    """SPART_FLAG_UNIFORM_GEOMETRY (shared sun/observer angles) must not change a single bit
+    pattern beyond rounding: compare with the general path and with the oracle."""
+    torch, sb, so = env
+    P = so.synthetic_params(3000, 2, seed=21)
+    P[:, so.SZA], P[:, so.VZA], P[:, so.RAA] = 33.0, 12.5, 140.0
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    a = sb.run_batch_params(dev, "Sentinel2A-MSI").cpu().numpy()
+    b = sb.run_batch_params(dev, "Sentinel2A-MSI", uniform_geometry=True).cpu().numpy()
+    assert relerr(b, a) < 1e-13
+    assert relerr(b, so.spart_bands(P, "Sentinel2A-MSI")) < RTOL64
+    c = sb.run_batch(P[:, 0:9], P[:, 9:15], P[:, 15:19], [33.0, 12.5, 140.0], P[:, 22:26], P[:, 26], "Sentinel2A-MSI")
+    assert np.array_equal(c, b)
+
+
 def test_cfg4_synthetic_fullspectrum_sensor(env):
     _, sb, so = env
     g = load_golden("batch_cfg4_SYNTH2001.npz")
