@@ -112,7 +112,6 @@ constexpr int kSampleThreads = 128;
 // The 32 x 12 (sample, angle) fixed-point iterations need between 1 and ~120 steps each, so
 // they are treated as a queue of 384 tasks: a lane that converges stores its F value and
 // takes the next task, which keeps all lanes busy until the queue drains.
-// sA/sB: this warp's 32 LIDFa/LIDFb values; sF: [12][kSampleThreads] cumulative values,
 // column = thread index in the block.
 __constant__ double c_theta2[12];   // 2 * (pi/180) * theta for theta = 10..80 step 10, 82..88 step 2
 
@@ -126,48 +125,54 @@ constexpr int kLidfSpw = SPART_LIDF_SPW;
 
 // Leaf inclination distribution for the kLidfSpw samples of a warp (sailh.py:351-398).
 // The (sample, angle) fixed-point iterations need between 1 and ~120 steps each, so they are
-// treated as a queue of 12 * kLidfSpw tasks: a lane that converges stores its result and goes
-// idle; as soon as SPART_LIDF_BATCH lanes are idle they all receive new tasks in one
-// warp-uniform hand-out (handing out per converged lane would execute the divergent
-// hand-out code on almost every step).  sA/sB: the warp's LIDFa/LIDFb values; sF: the
-// warp's [12][kLidfSpw] results, holding 2 y + theta2 (divided by pi on read-out).
-__device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, double* sF) {
+// treated as a queue of 12 * kLidfSpw tasks.  The hot loop is only "step if running"; a lane
+// that converges just clears `running` and keeps its result in registers.  As soon as
+// SPART_LIDF_BATCH lanes are idle they write their results and receive new tasks in one
+// hand-out (doing either per converged lane would execute divergent code on almost every
+// step).  sA/sB: the warp's LIDFa/LIDFb values.  Results F(theta) go straight to global
+// memory at out[ang * stride_ang + smp * stride_smp] (8-byte scattered writes, 96 B per
+// sample in total), so the kernel needs almost no shared memory; nvalid = number of real
+// samples of this warp.
+__device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, double* __restrict__ out,
+                                          int64_t stride_ang, int64_t stride_smp, int nvalid) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int ntask = 12 * kLidfSpw;
   int next = 32;                 // warp-uniform: first unassigned task; task t -> angle t / SPW, sample t % SPW
-  int slot = lane;               // sF index of the running task
+  int ang = 0, smp = lane;
   double a = sA[lane], b = sB[lane];
   double theta2 = c_theta2[0];
   double x = theta2, y = 0.0;
   bool running = true;
-  bool force = a > 1.0;          // sailh.py:371-372: closed form, no iteration
-  int guard = 0;
+  if (a > 1.0) {                 // sailh.py:371-372: closed form F = 1 - cos(theta), no iteration
+    y = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2)) - theta2);
+    running = false;
+  }
+  int iters = 0;                 // warp-uniform runaway guard (non-convergent garbage input)
   while (true) {
-    if (running) {
-      const bool done = dcum_step(a, b, theta2, x, y) || force || (++guard > 100000);
-      if (done) {
-        sF[slot] = force ? SPART_PI * (1.0 - cos(0.5 * theta2)) : (2.0 * y + theta2);
-        running = false;
-      }
-    }
+    if (running) running = !dcum_step(a, b, theta2, x, y);
     const unsigned idle = __ballot_sync(full, !running);
     const int nidle = __popc(idle);
     if (next < ntask) {
       if (nidle >= SPART_LIDF_BATCH) {
         if (!running) {
+          if (smp < nvalid) out[ang * stride_ang + smp * stride_smp] = (2.0 * y + theta2) * (1.0 / SPART_PI);
           const int task = next + __popc(idle & lt_mask);
           if (task < ntask) {
-            const int ang = task / kLidfSpw, smp = task % kLidfSpw;
-            slot = ang * kLidfSpw + smp;
+            ang = task / kLidfSpw;
+            smp = task % kLidfSpw;
             a = sA[smp];
             b = sB[smp];
-            force = a > 1.0;
             theta2 = c_theta2[ang];
             x = theta2;
-            guard = 0;
             running = true;
+            if (a > 1.0) {
+              y = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2)) - theta2);
+              running = false;
+            }
+          } else {
+            smp = kLidfSpw;      // nothing left to write for this lane
           }
         }
         next += nidle;
@@ -175,35 +180,58 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
     } else if (nidle == 32) {
       break;
     }
+    if (++iters > (1 << 22)) break;
   }
-  __syncwarp();
+  // every lane ends idle with its last result still in registers
+  if (smp < nvalid) out[ang * stride_ang + smp * stride_smp] = (2.0 * y + theta2) * (1.0 / SPART_PI);
 }
 
 // workspace rows: the per-sample record followed by the 12 cumulative leaf-angle values
 constexpr int kRowF = R_COUNT;
 constexpr int kWsRows = R_COUNT + 12;
 
+#ifndef SPART_LIDF_MINBLOCKS
+#define SPART_LIDF_MINBLOCKS 8
+#endif
+
 // Kernel 1: leaf inclination distribution (CanopyStructure.__init__, sailh.py:340-398).
-// A kernel of its own so that it runs at ~40 registers / 64 warps per SM: the iteration is
+// A kernel of its own so that it runs at ~54 registers / 36 warps per SM: the iteration is
 // one long dependent FP64 chain per lane and needs the occupancy to fill the FP64 pipe.
-__global__ void __launch_bounds__(kSampleThreads)
-lidf_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ ws) {
+// ab0/ab1: the LIDFa / LIDFb rows; F(theta_i) of sample s is written to
+// out[i * stride_ang + s * stride_smp].
+__global__ void __launch_bounds__(kSampleThreads, SPART_LIDF_MINBLOCKS)
+lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t n, double* __restrict__ out,
+            int64_t stride_ang, int64_t stride_smp) {
   constexpr int kWarps = kSampleThreads / 32;
-  __shared__ double sF[kWarps][12 * kLidfSpw];
   __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * kLidfSpw;   // first sample of this warp
   if (base >= n) return;
   for (int j = lane; j < kLidfSpw; j += 32) {
     const int64_t s = (base + j < n) ? base + j : n - 1;     // tail entries shadow the last sample
-    sA[warp][j] = P[P_LIDFA * ld + s];
-    sB[warp][j] = P[P_LIDFB * ld + s];
+    sA[warp][j] = ab0[s];
+    sB[warp][j] = ab1[s];
   }
   __syncwarp();
-  warp_lidf(sA[warp], sB[warp], sF[warp]);
-  for (int i = 0; i < 12; ++i)
-    for (int j = lane; j < kLidfSpw; j += 32)
-      if (base + j < n) ws[(size_t)(kRowF + i) * n + base + j] = sF[warp][i * kLidfSpw + j] * (1.0 / SPART_PI);
+  const int nvalid = (int)((n - base < kLidfSpw) ? (n - base) : kLidfSpw);
+  warp_lidf(sA[warp], sB[warp], out + base * stride_smp, stride_ang, stride_smp, nvalid);
+}
+
+// In-place F -> lidf = diff([0, F_1..F_12, 1]) on a [n][13] buffer whose first 12 entries per
+// sample hold the cumulative values (calculate_leafangles, sailh.py:387-396).
+__global__ void lidf_diff_kernel(double* __restrict__ out, int64_t n) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double F[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) F[i] = out[s * 13 + i];
+  double prev = 0.0;
+#pragma unroll
+  for (int i = 0; i < 13; ++i) {
+    const double Fi = (i < 12) ? F[i] : 1.0;
+    out[s * 13 + i] = Fi - prev;
+    prev = Fi;
+  }
 }
 
 // Kernel 2, one thread per sample: everything else that does not depend on wavelength or
@@ -488,33 +516,6 @@ spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   }
 }
 
-// Leaf inclination distribution only (CanopyStructure.lidf, sailh.py:340-398).
-__global__ void __launch_bounds__(kSampleThreads)
-leafangles_kernel(const double* __restrict__ ab, int64_t n, int64_t ld, double* __restrict__ out) {
-  constexpr int kWarps = kSampleThreads / 32;
-  __shared__ double sF[kWarps][12 * kLidfSpw];
-  __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * kLidfSpw;
-  if (base >= n) return;
-  for (int j = lane; j < kLidfSpw; j += 32) {
-    const int64_t s = (base + j < n) ? base + j : n - 1;
-    sA[warp][j] = ab[s];
-    sB[warp][j] = ab[ld + s];
-  }
-  __syncwarp();
-  warp_lidf(sA[warp], sB[warp], sF[warp]);
-  for (int j = lane; j < kLidfSpw; j += 32) {
-    if (base + j >= n) continue;
-    double Fprev = 0.0;
-    for (int i = 0; i < 13; ++i) {
-      const double Fi = (i < 12) ? sF[warp][i * kLidfSpw + j] * (1.0 / SPART_PI) : 1.0;
-      out[(size_t)(base + j) * 13 + i] = Fi - Fprev;
-      Fprev = Fi;
-    }
-  }
-}
-
 // ---- peak micro-benchmarks ---------------------------------------------------------------
 template <typename T>
 __global__ void fma_chain_kernel(T* out, int iters, T a, T b) {
@@ -690,7 +691,8 @@ size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n) {
 static int launch_lidf(const double* params_dev, int64_t n, int64_t ld, double* ws, cudaStream_t st) {
   const int64_t per_block = (int64_t)(kSampleThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, ws);
+  lidf_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev + P_LIDFA * ld, params_dev + P_LIDFB * ld, n,
+                                                 ws + (size_t)kRowF * n, n, 1);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
@@ -816,7 +818,10 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
   }
   const int64_t per_block = (int64_t)(kSampleThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  leafangles_kernel<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(ab_dev, n, ld, out_dev);
+  lidf_kernel<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(ab_dev, ab_dev + ld, n, out_dev, 1, 13);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  lidf_diff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, n);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
@@ -858,8 +863,10 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params
   std::lock_guard<std::mutex> lock(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));
   const int nb = ctx->n_bands[sensor];
-  // chunk so that three slots pipeline H2D / kernels / D2H; cap the per-slot output at ~256 MB
-  int64_t chunk = 1 << 18;
+  // chunk so that three slots pipeline H2D / kernels / D2H (64 Ki samples: ~14 MB in, ~20 MB out
+  // per chunk for 13 bands, small enough that pipeline fill/drain is a few percent of a 1M batch);
+  // cap the per-slot output at ~256 MB for many-band sensors
+  int64_t chunk = 1 << 16;
   const int64_t cap_by_out = ((int64_t)256 << 20) / ((int64_t)nb * SPART_NOUT * 8);
   if (chunk > cap_by_out) chunk = cap_by_out > 1024 ? cap_by_out : 1024;
   if (chunk > n) chunk = n;
