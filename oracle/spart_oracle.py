@@ -601,13 +601,14 @@ def canopy_spectra(params, opt=None, expint=_exp1):
                 rso=rso, rdo=rdo, rsd=rsd, rdd=rdd)
 
 
-def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1):
+def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_canopy=False):
     """SPART(...).run() (SPART.py:162-269) for a batch -> [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
 
     `sensor` is a sensor name or a sensorinfo dict.  faithful=True evaluates the whole
     2162-wavelength spectrum and calls np.interp / the gather-based SRF convolution like
     the reference does; faithful=False evaluates only the wavelengths np.interp touches
-    and uses the linearity of the SRF convolution in Ea (identical to ~1e-15)."""
+    and uses the linearity of the SRF convolution in Ea (identical to ~1e-15).
+    return_canopy=True also returns the band-sampled canopy reflectances [n, nb, 4]."""
     params = np.atleast_2d(np.asarray(params, dtype=np.float64))
     opt = opt or load_optical()
     if isinstance(sensor, str):
@@ -640,7 +641,12 @@ def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1):
         La = convEa[None, :] * scale
     atmo = smac(params[:, SZA:RAA + 1], params[:, AOT550:PA + 1], sensor["SMAC_coef"])
     R_TOC, R_TOA, L_TOA = toc_to_toa(rv["rso"], rv["rdo"], rv["rdd"], rv["rsd"], atmo, La)
-    return np.stack([R_TOC, R_TOA, L_TOA], axis=2)
+    out = np.stack([R_TOC, R_TOA, L_TOA], axis=2)
+    if return_canopy:
+        # band-sampled rso, rdo, rsd, rdd [n, nb, 4]: lets tests tell physically valid SAILH
+        # output (all four in (0, 1)) from the reference's out-of-range results
+        return out, np.stack([rv["rso"], rv["rdo"], rv["rsd"], rv["rdd"]], axis=2)
+    return out
 
 
 # ------------------------------------------------------------ synthetic sensor (config 4)

@@ -24,6 +24,7 @@
 
 #include "../../include/spart_b200.h"
 #include "spart_device.cuh"
+#include "spart_device_f32.cuh"
 
 using namespace spart;
 
@@ -468,6 +469,203 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   }
 }
 
+// ---- FP32 mode (SPART_FP32) -----------------------------------------------------------------
+// Two kernels: per-sample geometry (leaf angles by safeguarded Newton, volume scattering,
+// hot-spot integrals, soil / atmosphere scalars) and the band kernel.  The per-sample record
+// is kept as float [R_COUNT][n] in the same workspace; parameters are read as double and
+// results are written as double.
+__constant__ float c_sin_ttli_f[13];
+__constant__ float c_cos_ttli_f[13];
+__constant__ float c_theta2_f[12];
+
+__global__ void __launch_bounds__(kSampleThreads)
+geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* __restrict__ rec,
+                    int uniform_geometry) {
+  using namespace spart::f32;
+  __shared__ float s_cls[13][4];
+  const int tid = threadIdx.x;
+  const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
+  const bool valid = s_raw < n;
+  const int64_t s = valid ? s_raw : n - 1;
+
+  const double tts_d = P[P_SZA * ld + s], tto_d = P[P_VZA * ld + s], rel_d = P[P_RAA * ld + s];
+  const float tts = (float)tts_d, tto = (float)tto_d, rel = (float)rel_d;
+  const float psi = fabsf(rel - 360.0f * rintf(rel / 360.0f));
+  const float psi_rad = psi * (SPART_PI_F / 180.0f);
+  float sin_tts, cos_tts, sin_tto, cos_tto;
+  sincosf(tts * (SPART_PI_F / 180.0f), &sin_tts, &cos_tts);
+  sincosf(tto * (SPART_PI_F / 180.0f), &sin_tto, &cos_tto);
+  const float tan_tts = sin_tts / cos_tts, tan_tto = sin_tto / cos_tto;
+  const float cos_psi = cosf(psi_rad);
+  const float dso = sqrtf(fmaxf(0.0f, tan_tts * tan_tts + tan_tto * tan_tto - 2.0f * tan_tts * tan_tto * cos_psi));
+  const float inv_cc = SPART_PI_F / (cos_tts * cos_tto);
+  const float inv_cs = 1.0f / cos_tts, inv_co = 1.0f / cos_tto;
+
+  if (uniform_geometry) {
+    if (tid < 13) {
+      float chi_s, chi_o, frho, ftau;
+      volscatt_class_f(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli_f[tid], c_cos_ttli_f[tid],
+                       chi_s, chi_o, frho, ftau);
+      s_cls[tid][0] = chi_s * inv_cs;
+      s_cls[tid][1] = chi_o * inv_co;
+      s_cls[tid][2] = frho * inv_cc;
+      s_cls[tid][3] = ftau * inv_cc;
+    }
+    __syncthreads();
+  }
+  if (!valid) return;
+
+  const float a = (float)P[P_LIDFA * ld + s], b = (float)P[P_LIDFB * ld + s];
+  float k = 0.0f, K = 0.0f, bf = 0.0f, sob = 0.0f, sof = 0.0f;
+  float Fprev = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < 13; ++i) {
+    const float Fi = (i < 12) ? dcum_newton_f(a, b, c_theta2_f[i]) : 1.0f;
+    const float lidf = Fi - Fprev;
+    Fprev = Fi;
+    float ksli, koli, sobli, sofli;
+    if (uniform_geometry) {
+      ksli = s_cls[i][0]; koli = s_cls[i][1]; sobli = s_cls[i][2]; sofli = s_cls[i][3];
+    } else {
+      float chi_s, chi_o, frho, ftau;
+      volscatt_class_f(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli_f[i], c_cos_ttli_f[i], chi_s,
+                       chi_o, frho, ftau);
+      ksli = chi_s * inv_cs; koli = chi_o * inv_co; sobli = frho * inv_cc; sofli = ftau * inv_cc;
+    }
+    k += ksli * lidf;
+    K += koli * lidf;
+    bf += (c_cos_ttli_f[i] * c_cos_ttli_f[i]) * lidf;
+    sob += sobli * lidf;
+    sof += sofli * lidf;
+  }
+
+  const float LAI = (float)P[P_LAI * ld + s], q = (float)P[P_Q * ld + s];
+  float sumpso, pso2w;
+  hotspot_integrals_f(K, k, LAI, q, dso, sumpso, pso2w);
+  const float tau_ss = __expf(-k * LAI), tau_oo = __expf(-K * LAI);
+  rec[R_K_SUN * n + s] = k;
+  rec[R_K_OBS * n + s] = K;
+  rec[R_BF * n + s] = bf;
+  rec[R_SOB * n + s] = sob;
+  rec[R_SOF * n + s] = sof;
+  rec[R_TAUSS * n + s] = tau_ss;
+  rec[R_TAUOO * n + s] = tau_oo;
+  rec[R_SUMPSO * n + s] = sumpso;
+  rec[R_PSO2W * n + s] = pso2w;
+  rec[R_Z * n + s] = one_minus_exp(-(k + K) * LAI) / (K + k);
+
+  {
+    const float B = (float)P[P_B * ld + s];
+    float slat, clat, slon, clon;
+    sincosf((float)P[P_LAT * ld + s] * (SPART_PI_F / 180.0f), &slat, &clat);
+    sincosf((float)P[P_LON * ld + s] * (SPART_PI_F / 180.0f), &slon, &clon);
+    rec[R_F1 * n + s] = B * slat;
+    rec[R_F2 * n + s] = B * clat * slon;
+    rec[R_F3 * n + s] = B * clat * clon;
+    const float mu = ((float)P[P_SMP * ld + s] - 5.0f) / (float)P[P_SMC * ld + s];
+    rec[R_MU * n + s] = mu;
+    rec[R_EMU * n + s] = __expf(-mu);
+  }
+
+  {
+    // the scattering-angle terms keep FP64: cos(rel * 180/pi) has an argument of ~1e4 rad (smac.py:130)
+    const double us_d = cos(tts_d * SPART_DEG2RAD), uv_d = cos(tto_d * SPART_DEG2RAD);
+    const double crd = 180.0 / SPART_PI;
+    double cksi = -((us_d * uv_d) + (sqrt(1.0 - us_d * us_d) * sqrt(1.0 - uv_d * uv_d) * cos(rel_d * crd)));
+    if (cksi < -1.0) cksi = -1.0;
+    const float us = (float)us_d, uv = (float)uv_d;
+    const float Peq = (float)(P[P_PA * ld + s] / 1013.25);
+    const float m = 1.0f / us + 1.0f / uv;
+    rec[R_US * n + s] = us;
+    rec[R_UV * n + s] = uv;
+    rec[R_M * n + s] = m;
+    rec[R_PEQ * n + s] = Peq;
+    rec[R_LO3 * n + s] = logf((float)P[P_UO3 * ld + s] * m);
+    rec[R_LH2O * n + s] = logf((float)P[P_UH2O * ld + s] * m);
+    rec[R_LM * n + s] = logf(m);
+    rec[R_LPEQ * n + s] = (float)log(P[P_PA * ld + s] / 1013.25);   // ln of a number close to 1
+    rec[R_CKSI * n + s] = (float)cksi;
+    rec[R_KSID * n + s] = (float)(crd * acos(cksi));
+    rec[R_RAYPH * n + s] = (float)(0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742);
+    rec[R_INVUS * n + s] = 1.0f / us;
+    rec[R_INVUV * n + s] = 1.0f / uv;
+    rec[R_INV1PUS * n + s] = 1.0f / (1.0f + us);
+    rec[R_INV1PUV * n + s] = 1.0f / (1.0f + uv);
+    rec[R_AA3 * n + s] = us * uv / (us + uv);
+    const float bb = 2.0f * SPART_PI_F * (float)P[P_DOY * ld + s] / 365.0f;
+    float sb, cb, s2b, c2b;
+    sincosf(bb, &sb, &cb);
+    sincosf(2.0f * bb, &s2b, &c2b);
+    const float cf = 1.00011f + 0.034221f * cb + 0.00128f * sb + 0.000719f * c2b + 0.000077f * s2b;
+    rec[R_ETSCALE * n + s] = cf * us / SPART_PI_F;
+  }
+}
+
+__global__ void __launch_bounds__(kBandThreads)
+band_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, const float* __restrict__ rec,
+                const double* __restrict__ band_table, int nb, double* __restrict__ out) {
+  using namespace spart::f32;
+  __shared__ TauTableF s_tau;
+  __shared__ float s_bt[kBandChunk][BT_COUNT];
+  const int b0 = blockIdx.x * kBandChunk;
+  const int nbc = min(kBandChunk, nb - b0);
+  load_tau_table_f(&s_tau);
+  for (int i = threadIdx.x; i < nbc * BT_COUNT; i += blockDim.x)
+    (&s_bt[0][0])[i] = (float)band_table[(size_t)b0 * BT_COUNT + i];
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
+  if (s >= n) return;
+
+  const LeafParF L = load_leaf_f(P, ld, s);
+  SoilParF S;
+  S.f1 = rec[R_F1 * n + s]; S.f2 = rec[R_F2 * n + s]; S.f3 = rec[R_F3 * n + s];
+  S.mu = rec[R_MU * n + s]; S.emu = rec[R_EMU * n + s]; S.film = (float)P[P_FILM * ld + s];
+  CanopyGeoF G;
+  G.LAI = (float)P[P_LAI * ld + s];
+  G.k = rec[R_K_SUN * n + s]; G.K = rec[R_K_OBS * n + s]; G.bf = rec[R_BF * n + s];
+  G.sob = rec[R_SOB * n + s]; G.sof = rec[R_SOF * n + s];
+  G.tau_ss = rec[R_TAUSS * n + s]; G.tau_oo = rec[R_TAUOO * n + s];
+  G.sumpso = rec[R_SUMPSO * n + s]; G.pso2w = rec[R_PSO2W * n + s]; G.Z = rec[R_Z * n + s];
+  AtmSampleF A;
+  A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
+  A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s]; A.lpeq = rec[R_LPEQ * n + s];
+  A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
+  A.taup550 = (float)P[P_AOT * ld + s];
+  A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
+  A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
+  const float etscale = rec[R_ETSCALE * n + s];
+  double* o = out + ((size_t)s * nb + b0) * SPART_NOUT;
+
+#pragma unroll 1
+  for (int bi = 0; bi < nbc; ++bi) {
+    const float* bt = s_bt[bi];
+    float rso = 0.0f, rdo = 0.0f, rsd = 0.0f, rdd = 0.0f;
+    const int npts = (bt[BT_NPTS] > 1.5f) ? 2 : 1;
+#pragma unroll 1
+    for (int pt = 0; pt < npts; ++pt) {
+      const float* lc = &bt[BT_LC0 + pt * LC_COUNT];
+      float refl, tran, a0, a1, a2, a3;
+      prospect_point_f(L, lc, &s_tau, refl, tran);
+      const float rwet = bsm_point_f(S, lc);
+      sailh_point_f(G, refl, tran, rwet, a0, a1, a2, a3);
+      if (pt == 0) {
+        rso = a0; rdo = a1; rsd = a2; rdd = a3;
+      } else {
+        const float fr = bt[BT_FRAC];
+        rso = (a0 - rso) * fr + rso;
+        rdo = (a1 - rdo) * fr + rdo;
+        rsd = (a2 - rsd) * fr + rsd;
+        rdd = (a3 - rdd) * fr + rdd;
+      }
+    }
+    float R_TOC, R_TOA, L_TOA;
+    smac_toa_band_f(A, &bt[BT_SMAC], bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
+    o[bi * SPART_NOUT + 0] = (double)R_TOC;
+    o[bi * SPART_NOUT + 1] = (double)R_TOA;
+    o[bi * SPART_NOUT + 2] = (double)L_TOA;
+  }
+}
+
 // Full-spectrum planes: blockIdx.x = chunk of kSpecChunk wavelengths, blockIdx.y = sample tile.
 constexpr int kSpecThreads = 128;
 constexpr int kSpecChunk = 32;
@@ -583,6 +781,17 @@ static int init_device_constants(int device) {
     th2[i] = 2.0 * (M_PI / 180.0) * theta;
   }
   CUDA_TRY(cudaMemcpyToSymbol(c_theta2, th2, sizeof(th2)));
+  {
+    float th2f[12], slf[13], clf[13];
+    for (int i = 0; i < 12; ++i) th2f[i] = (float)th2[i];
+    for (int i = 0; i < 13; ++i) {
+      slf[i] = (float)sl[i];
+      clf[i] = (float)cl[i];
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_theta2_f, th2f, sizeof(th2f)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_sin_ttli_f, slf, sizeof(slf)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_cos_ttli_f, clf, sizeof(clf)));
+  }
   CUDA_TRY(cudaMemcpyToSymbol(c_sin_ttli, sl, sizeof(sl)));
   CUDA_TRY(cudaMemcpyToSymbol(c_cos_ttli, cl, sizeof(cl)));
 
@@ -721,8 +930,8 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
   int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_forward_bands");
   if (rc) return rc;
   if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "spart_forward_bands: unknown sensor%s");
-  if (precision != SPART_FP64)
-    return fail(SPART_EINVAL, "spart_forward_bands: only SPART_FP64 is implemented in this build%s");
+  if (precision != SPART_FP64 && precision != SPART_FP32)
+    return fail(SPART_EINVAL, "spart_forward_bands: precision must be SPART_FP64 or SPART_FP32%s");
   if (n == 0) return SPART_OK;
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
@@ -740,16 +949,28 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
       }
     }
   }
-  if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
-  rc = launch_lidf(params_dev, n, ld, rec, st);
-  if (rc) return rc;
-  if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
-  rc = launch_geometry(params_dev, n, ld, rec, (flags & SPART_FLAG_UNIFORM_GEOMETRY) ? 1 : 0, st);
-  if (rc) return rc;
-  if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
+  const int uniform = (flags & SPART_FLAG_UNIFORM_GEOMETRY) ? 1 : 0;
   const int nb = ctx->n_bands[sensor];
   dim3 grid((unsigned)((nb + kBandChunk - 1) / kBandChunk), (unsigned)((n + kBandThreads - 1) / kBandThreads));
-  band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+  if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
+  if (precision == SPART_FP64) {
+    rc = launch_lidf(params_dev, n, ld, rec, st);
+    if (rc) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
+    rc = launch_geometry(params_dev, n, ld, rec, uniform, st);
+    if (rc) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
+    band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+  } else {   // SPART_FP32: the leaf angles are solved inside the geometry kernel
+    if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
+    const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+    geometry_kernel_f32<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, (float*)rec, uniform);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
+    band_kernel_f32<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, (const float*)rec, ctx->d_band[sensor], nb,
+                                                    out_dev);
+  }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   if (prof) {
@@ -857,8 +1078,8 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params
   if (n < 0 || ld < n) return fail(SPART_EINVAL, "spart_forward_bands_host: need 0 <= n <= ld%s");
   if (sensor < 0 || sensor >= ctx->n_sensors)
     return fail(SPART_EINVAL, "spart_forward_bands_host: unknown sensor%s");
-  if (precision != SPART_FP64)
-    return fail(SPART_EINVAL, "spart_forward_bands_host: only SPART_FP64 is implemented in this build%s");
+  if (precision != SPART_FP64 && precision != SPART_FP32)
+    return fail(SPART_EINVAL, "spart_forward_bands_host: precision must be SPART_FP64 or SPART_FP32%s");
   if (n == 0) return SPART_OK;
   std::lock_guard<std::mutex> lock(ctx->mu);
   CUDA_TRY(cudaSetDevice(ctx->device));

@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 from conftest import load_golden, relerr  # noqa: E402
 
 RTOL64 = 1e-9
+RTOL32 = 1e-4      # FP32 mode (BASELINE.json north_star)
 
 
 @pytest.fixture(scope="module")
@@ -24,10 +25,10 @@ def env():
     return torch, spart_b200, so
 
 
-def gpu_bands(env, P, sensor):
+def gpu_bands(env, P, sensor, precision="fp64"):
     torch, sb, _ = env
     dev = torch.from_numpy(np.ascontiguousarray(np.asarray(P, dtype=np.float64).T)).cuda()
-    out = sb.run_batch_params(dev, sensor)
+    out = sb.run_batch_params(dev, sensor, precision=precision)
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -50,6 +51,76 @@ def test_bands_vs_oracle_random(env, sensor, cfg):
     want = so.spart_bands(P, sensor)
     got = gpu_bands(env, P, sensor)
     assert relerr(got, want) < RTOL64
+
+
+def _fp32_report(env, P, sensor):
+    _, _, so = env
+    want, canopy = so.spart_bands(P, sensor, return_canopy=True)
+    got = gpu_bands(env, P, sensor, precision="fp32")
+    with np.errstate(all="ignore"):
+        e = np.abs(got - want) / np.abs(want)
+    # physically valid SAILH output: all four canopy reflectances inside (0, 1).  Outside that
+    # range (the reference returns rso < 0 or rdd > 1 for near-conservative leaves under dense
+    # canopies) R_TOC is a difference of O(1) terms and no single-precision evaluation can be
+    # relatively accurate.
+    valid = ((canopy > 0) & (canopy < 1)).all(axis=2)
+    return got, want, e, valid
+
+
+@pytest.mark.parametrize("sensor,cfg", [("Sentinel2A-MSI", 2), ("Sentinel2B-MSI", 5), ("LANDSAT7-ETM", 2),
+                                        ("Sentinel2A-MSI", 4)])
+def test_fp32_mode_lut_configs(env, sensor, cfg):
+    """FP32 mode on the fixed-geometry LUT distributions of BASELINE.json (configs 2, 4, 5):
+    relative error <= 1e-4 on EVERY output against the FP64 oracle."""
+    _, _, so = env
+    P = so.synthetic_params(50000, cfg, seed=2000 + cfg)
+    got, want, e, valid = _fp32_report(env, P, sensor)
+    assert np.isfinite(got).all()
+    assert e.max() < RTOL32
+
+
+@pytest.mark.parametrize("sensor", ["LANDSAT8-OLI", "TerraAqua-MODIS", "Sentinel3A-OLCI"])
+def test_fp32_mode_random_geometry(env, sensor):
+    """FP32 mode with random sun/view angles and PROSPECT-PRO leaves (config 3).  Leaves with
+    rho + tau > 0.98 under LAI > 5 make the canopy solution ill-conditioned in 1 - rho - tau, so
+    the gate is: >= 99.99 % of the physically valid outputs within 1e-4, all of them within 1e-3."""
+    _, _, so = env
+    P = so.synthetic_params(50000, 3, seed=2003)
+    got, want, e, valid = _fp32_report(env, P, sensor)
+    assert valid.mean() > 0.99
+    ev = e[valid]
+    assert (ev < RTOL32).mean() >= 0.9999
+    assert ev.max() < 1e-3
+
+
+def test_fp32_mode_goldens_and_edges(env):
+    _, sb, so = env
+    for name in ("cfg2_S2A", "cfg5_S2B"):
+        g = load_golden(f"batch_{name}.npz")
+        got = gpu_bands(env, g["params"], str(g["sensor"]), precision="fp32")
+        assert relerr(got, g["O1"]) < RTOL32
+    P = so.synthetic_params(64, 2, seed=77)
+    P[0:8, so.SMP] = [0.0, 4.99, 5.0, 5.01, 3.0, 1.0, 5.0, 2.0]                 # dry-soil branch
+    P[8:16, so.PROT], P[8:16, so.CBC] = 0.001, 0.004                           # PROSPECT-PRO switch (Cdm > 0)
+    P[16:24, so.SZA], P[16:24, so.VZA] = 30.0, 30.0                            # exact hot spot
+    P[24:28, so.RAA] = [180.0, 360.0, 540.0, 270.0]
+    P[28:32, so.SZA] = 0.0
+    P[32:36, so.LAI] = [1e-2, 0.05, 10.0, 15.0]
+    P[36:40, so.SZA] = 30.0
+    P[36:40, so.VZA] = 30.0 + np.array([1e-4, 1e-3, 1e-2, 0.1])                # almost in the hot spot
+    got, want, e, valid = _fp32_report(env, P, "LANDSAT8-OLI")
+    assert np.isfinite(got).all()
+    rows = np.repeat(np.arange(64)[:, None], e.shape[1], 1)[valid]
+    ev = e[valid].max(axis=1)
+    assert ev[rows < 32].max() < RTOL32          # branch / geometry edge cases
+    assert ev.max() < 3e-4                       # LAI 0.01 ... 15 and the 1e-4 degree near-hot-spot rows
+    # uniform-geometry flag and host path in FP32 mode
+    P = so.synthetic_params(3000, 2, seed=5)
+    pt = np.ascontiguousarray(P.T)
+    a = sb.run_batch_params(pt, "Sentinel2A-MSI", precision="fp32")
+    b = sb.run_batch_params(pt, "Sentinel2A-MSI", precision="fp32", uniform_geometry=True)
+    assert relerr(b, a) < 1e-5
+    assert relerr(b, so.spart_bands(P, "Sentinel2A-MSI")) < RTOL32
 
 
 def test_e2e_defaults_all_sensors(env):

@@ -27,17 +27,18 @@ if len(sys.argv) > 3 and sys.argv[3] == "3":      # random geometry
     P[21] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 180
 _, st = eng.sensor(sensor)
 out = torch.empty((n, st.n_bands, 3), dtype=torch.float64, device=dev)
+precision = sys.argv[4] if len(sys.argv) > 4 else "fp64"
 uniform = not (len(sys.argv) > 3 and sys.argv[3] == "3") and os.environ.get("SPART_NO_UNIFORM") is None
 for _ in range(3):
-    eng.forward_bands(P, sensor, out=out, uniform_geometry=uniform)
+    eng.forward_bands(P, sensor, out=out, uniform_geometry=uniform, precision=precision)
 torch.cuda.synchronize()
 eng.profile_enable(sensor, True)
 for _ in range(8):
-    eng.forward_bands(P, sensor, out=out, uniform_geometry=uniform)
+    eng.forward_bands(P, sensor, out=out, uniform_geometry=uniform, precision=precision)
 torch.cuda.synchronize()
 r = eng.profile_read(sensor)
 c = r["calls"]
 print(json.dumps({"lib": os.environ.get("SPART_B200_LIB", "default"), "n": n, "sensor": sensor,
-                  "uniform": uniform, "lidf_ms": r["lidf_ms"] / c, "geometry_ms": r["geometry_ms"] / c,
+                  "uniform": uniform, "precision": precision, "lidf_ms": r["lidf_ms"] / c, "geometry_ms": r["geometry_ms"] / c,
                   "band_ms": r["band_ms"] / c,
                   "checksum": float(out.sum().item())}))
