@@ -235,6 +235,37 @@ def run_ours(args):
     eng.profile_enable(SENSOR, False)
     value = world * n * args.steps / (ms * 1e-3)
 
+    # --- FP32 mode on the same batch (reported beside the FP64 headline) ------------------
+    out32 = torch.empty_like(out)
+    for _ in range(args.warmup):
+        eng.forward_bands(params, SENSOR, out=out32, uniform_geometry=True, precision="fp32")
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        eng.forward_bands(params, SENSOR, out=out32, uniform_geometry=True, precision="fp32")
+    f1.record()
+    barrier()
+    ms32 = max_over_ranks(f0.elapsed_time(f1))
+    err32 = float(((out32 - out).abs() / out.abs()).max().item())
+
+    # --- final gather of the per-rank results (the only collective of the path) -----------
+    gather = None
+    if world > 1:
+        from spart_b200.distributed import gather_results
+        for _ in range(2):
+            gather_results(out, world * n, dst=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        full = gather_results(out, world * n, dst=0)
+        g1.record()
+        barrier()
+        gms = max_over_ranks(g0.elapsed_time(g1))
+        gather = {"ms": gms, "bytes_to_root": (world - 1) * n * nb * 3 * 8,
+                  "gb_per_s": (world - 1) * n * nb * 3 * 8 / (gms * 1e-3) / 1e9, "op": "nccl gather to rank 0"}
+        del full
+
     # --- end to end through the public host-buffer API ---------------------------------
     host_in = torch.empty((27, n), dtype=torch.float64).pin_memory()
     host_in.copy_(params)
@@ -307,6 +338,9 @@ def run_ours(args):
         "roofline": roofline, "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,
         "peaks": peaks,
+        "fp32_mode": {"value": world * n * args.steps / (ms32 * 1e-3), "unit": "simulations/s",
+                      "ms_per_step": ms32 / args.steps, "max_rel_err_vs_fp64": err32},
+        "gather": gather,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SPART_ABI_VERSION 2
+#define SPART_ABI_VERSION 3
 
 #define SPART_NPAR 27       /* rows of a parameter batch                                   */
 #define SPART_NWL 2001      /* 400..2400 nm, 1 nm (SpectralBands.wlP, SPART.py:303)        */
@@ -65,7 +65,11 @@ enum {
   /* the caller guarantees that rows 19..21 (sun / observer angles) are constant over the batch,
    * as in a look-up table for one acquisition geometry; the sample-independent volume-scattering
    * terms (_volscatt, sailh.py:401-446) are then evaluated once per thread block */
-  SPART_FLAG_UNIFORM_GEOMETRY = 1
+  SPART_FLAG_UNIFORM_GEOMETRY = 1,
+  /* the context was created with a user-supplied dry-soil spectrum in row 11 of SpartTables.lc
+   * (rows 12, 13 zero): B / lat / lon are ignored and rdry = that spectrum, as with the reference's
+   * SoilParametersFromFile (bsm.py:42-43, 155-226) */
+  SPART_FLAG_SOIL_SPECTRUM = 2
 };
 
 typedef struct SpartCtx SpartCtx;
@@ -135,7 +139,7 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params
  *   0 leaf refl  1 leaf tran  2 kChlrel (0 beyond 2400 nm)  3 soil refl (wet)  4 soil refl dry
  *   (value at 2400 nm beyond)  5 rso  6 rdo  7 rsd  8 rdd. */
 int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
-                           void* workspace_dev, double* out_dev, void* stream);
+                           int32_t flags, void* workspace_dev, double* out_dev, void* stream);
 
 /* Replaces CanopyStructure.__init__'s calculate_leafangles (sailh.py:340-398): the 13-class
  * leaf inclination distribution for n (LIDFa, LIDFb) pairs.  ab_dev: double [2][ld];

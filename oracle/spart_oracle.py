@@ -190,8 +190,9 @@ def _poisson_pmf(k, mu):
     return np.exp(-mu) * mu ** k / fact
 
 
-def bsm(soil, opt, idx=None):
+def bsm(soil, opt, idx=None, rdry_user=None):
     """BSM soil reflectance (bsm.py:17-128), batched.  soil: [n, 6] B lat lon SMp SMC film.
+    rdry_user: optional dry-soil spectrum [2001] replacing the soil-vector model (bsm.py:42-43).
     Returns (rwet, rdry), each [n, nl]."""
     if idx is None:
         idx = np.arange(NWL_P)
@@ -202,6 +203,8 @@ def bsm(soil, opt, idx=None):
     f2 = B * np.cos(lat * np.pi / 180) * np.sin(lon * np.pi / 180)
     f3 = B * np.cos(lat * np.pi / 180) * np.cos(lon * np.pi / 180)
     rdry = f1 * GSV[idx, 0][None, :] + f2 * GSV[idx, 1][None, :] + f3 * GSV[idx, 2][None, :]
+    if rdry_user is not None:
+        rdry = np.repeat(np.asarray(rdry_user, dtype=np.float64).reshape(-1)[idx][None, :], soil.shape[0], axis=0)
     kw = _col(opt["Kw"], idx)
     nw = _col(opt["nw"], idx)
 
@@ -588,20 +591,20 @@ def toc_to_toa(rv_so, rv_do, rv_dd, rv_sd, atmo, La):
     return R_TOC, R_TOA, L_TOA
 
 
-def canopy_spectra(params, opt=None, expint=_exp1):
+def canopy_spectra(params, opt=None, expint=_exp1, soil_rdry=None):
     """leafopt/soilopt/canopyopt of SPART.run() (SPART.py:189-214) over all 2162
     wavelengths.  Returns dict of [n, 2162] arrays (kChlrel [n, 2001])."""
     params = np.atleast_2d(np.asarray(params, dtype=np.float64))
     opt = opt or load_optical()
     refl, tran, kchl = prospect(params[:, CAB:CBC + 1], opt, expint=expint)
-    rwet, rdry = bsm(params[:, SOIL_B:FILM + 1], opt)
+    rwet, rdry = bsm(params[:, SOIL_B:FILM + 1], opt, rdry_user=soil_rdry)
     rho, tau, rs = pad_leaf(refl), pad_leaf(tran), pad_soil(rwet)
     rso, rdo, rsd, rdd = sailh(rs, rho, tau, params[:, LAI:HOT_Q + 1], params[:, SZA:RAA + 1])
     return dict(leaf_refl=rho, leaf_tran=tau, kChlrel=kchl, soil_refl=rs, soil_refl_dry=rdry,
                 rso=rso, rdo=rdo, rsd=rsd, rdd=rdd)
 
 
-def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_canopy=False):
+def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_canopy=False, soil_rdry=None):
     """SPART(...).run() (SPART.py:162-269) for a batch -> [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
 
     `sensor` is a sensor name or a sensorinfo dict.  faithful=True evaluates the whole
@@ -615,7 +618,7 @@ def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_c
         sensor = load_sensor(sensor)
     wl = sensor["wl_smac"].T[0]
     if faithful:
-        cs = canopy_spectra(params, opt, expint=expint)
+        cs = canopy_spectra(params, opt, expint=expint, soil_rdry=soil_rdry)
         wlS = spectral_wlS()
         rv = {k: np.stack([np.interp(wl, wlS, row) for row in cs[k]]) for k in ("rso", "rdo", "rdd", "rsd")}
         La = et_band_radiance(params[:, DOY], params[:, SZA], opt, sensor)
@@ -625,7 +628,7 @@ def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_c
             raise ValueError("band centres beyond 2400 nm need faithful=True")
         idx = np.concatenate([lo, hi])
         refl, tran, _ = prospect(params[:, CAB:CBC + 1], opt, idx, expint=expint)
-        rwet, _ = bsm(params[:, SOIL_B:FILM + 1], opt, idx)
+        rwet, _ = bsm(params[:, SOIL_B:FILM + 1], opt, idx, rdry_user=soil_rdry)
         r4 = sailh(rwet, refl, tran, params[:, LAI:HOT_Q + 1], params[:, SZA:RAA + 1])
         nb = lo.shape[0]
         rv = {}

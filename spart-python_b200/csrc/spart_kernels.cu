@@ -240,8 +240,9 @@ __global__ void lidf_diff_kernel(double* __restrict__ out, int64_t n) {
 // for one acquisition geometry): the 13-class volume-scattering terms are then evaluated
 // once per block by 13 threads instead of once per sample.
 __global__ void __launch_bounds__(kSampleThreads, SPART_SAMPLE_MINBLOCKS)
-geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec,
-                int uniform_geometry) {
+geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec, int flags) {
+  const int uniform_geometry = flags & SPART_FLAG_UNIFORM_GEOMETRY;
+  const bool soil_spectrum = (flags & SPART_FLAG_SOIL_SPECTRUM) != 0;
   __shared__ double s_cls[13][4];   // ksli, koli, sobli, sofli per leaf-inclination class
   const int tid = threadIdx.x;
   const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
@@ -321,9 +322,11 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     double slat, clat, slon, clon;
     sincos(P[P_LAT * ld + s] * SPART_PI / 180.0, &slat, &clat);
     sincos(P[P_LON * ld + s] * SPART_PI / 180.0, &slon, &clon);
-    rec[R_F1 * n + s] = B * slat;
-    rec[R_F2 * n + s] = B * clat * slon;
-    rec[R_F3 * n + s] = B * clat * clon;
+    // with a user-supplied dry-soil spectrum (bsm.py:42-43) the context's first soil vector IS that
+    // spectrum and the weights are (1, 0, 0): rdry = 1 * spectrum + 0 + 0 exactly
+    rec[R_F1 * n + s] = soil_spectrum ? 1.0 : B * slat;
+    rec[R_F2 * n + s] = soil_spectrum ? 0.0 : B * clat * slon;
+    rec[R_F3 * n + s] = soil_spectrum ? 0.0 : B * clat * clon;
     const double mu = (P[P_SMP * ld + s] - 5.0) / P[P_SMC * ld + s];
     rec[R_MU * n + s] = mu;
     rec[R_EMU * n + s] = exp_fast(-mu);
@@ -479,9 +482,10 @@ __constant__ float c_cos_ttli_f[13];
 __constant__ float c_theta2_f[12];
 
 __global__ void __launch_bounds__(kSampleThreads)
-geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* __restrict__ rec,
-                    int uniform_geometry) {
+geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* __restrict__ rec, int flags) {
   using namespace spart::f32;
+  const int uniform_geometry = flags & SPART_FLAG_UNIFORM_GEOMETRY;
+  const bool soil_spectrum = (flags & SPART_FLAG_SOIL_SPECTRUM) != 0;
   __shared__ float s_cls[13][4];
   const int tid = threadIdx.x;
   const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
@@ -559,9 +563,11 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
     float slat, clat, slon, clon;
     sincosf((float)P[P_LAT * ld + s] * (SPART_PI_F / 180.0f), &slat, &clat);
     sincosf((float)P[P_LON * ld + s] * (SPART_PI_F / 180.0f), &slon, &clon);
-    rec[R_F1 * n + s] = B * slat;
-    rec[R_F2 * n + s] = B * clat * slon;
-    rec[R_F3 * n + s] = B * clat * clon;
+    // with a user-supplied dry-soil spectrum (bsm.py:42-43) the context's first soil vector IS that
+    // spectrum and the weights are (1, 0, 0): rdry = 1 * spectrum + 0 + 0 exactly
+    rec[R_F1 * n + s] = soil_spectrum ? 1.0f : B * slat;
+    rec[R_F2 * n + s] = soil_spectrum ? 0.0f : B * clat * slon;
+    rec[R_F3 * n + s] = soil_spectrum ? 0.0f : B * clat * clon;
     const float mu = ((float)P[P_SMP * ld + s] - 5.0f) / (float)P[P_SMC * ld + s];
     rec[R_MU * n + s] = mu;
     rec[R_EMU * n + s] = __expf(-mu);
@@ -907,10 +913,10 @@ static int launch_lidf(const double* params_dev, int64_t n, int64_t ld, double* 
   return SPART_OK;
 }
 
-static int launch_geometry(const double* params_dev, int64_t n, int64_t ld, double* ws, int uniform,
+static int launch_geometry(const double* params_dev, int64_t n, int64_t ld, double* ws, int flags,
                            cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
-  geometry_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, ws, uniform);
+  geometry_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, ws, flags);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
@@ -949,7 +955,6 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
       }
     }
   }
-  const int uniform = (flags & SPART_FLAG_UNIFORM_GEOMETRY) ? 1 : 0;
   const int nb = ctx->n_bands[sensor];
   dim3 grid((unsigned)((nb + kBandChunk - 1) / kBandChunk), (unsigned)((n + kBandThreads - 1) / kBandThreads));
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
@@ -957,14 +962,14 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
     rc = launch_lidf(params_dev, n, ld, rec, st);
     if (rc) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
-    rc = launch_geometry(params_dev, n, ld, rec, uniform, st);
+    rc = launch_geometry(params_dev, n, ld, rec, flags, st);
     if (rc) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
     band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
   } else {   // SPART_FP32: the leaf angles are solved inside the geometry kernel
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
     const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
-    geometry_kernel_f32<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, (float*)rec, uniform);
+    geometry_kernel_f32<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, (float*)rec, flags);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
@@ -1009,7 +1014,7 @@ int spart_profile_read(SpartCtx* ctx, double* kernel_ms, int64_t* calls) {
   return SPART_OK;
 }
 
-int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
+int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld, int32_t flags,
                            void* workspace_dev, double* out_dev, void* stream) {
   int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_forward_spectrum");
   if (rc) return rc;
@@ -1018,7 +1023,7 @@ int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_
   double* rec = (double*)workspace_dev;
   rc = launch_lidf(params_dev, n, ld, rec, st);
   if (rc) return rc;
-  rc = launch_geometry(params_dev, n, ld, rec, 0, st);
+  rc = launch_geometry(params_dev, n, ld, rec, flags & ~SPART_FLAG_UNIFORM_GEOMETRY, st);
   if (rc) return rc;
   dim3 grid((SPART_NWL_S + kSpecChunk - 1) / kSpecChunk, (unsigned)((n + kSpecThreads - 1) / kSpecThreads));
   spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, out_dev);

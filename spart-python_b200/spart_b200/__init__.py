@@ -8,11 +8,12 @@ from ._lib import SpartError
 from .batch import pack_batch, row_as_dataframe, run_batch, run_batch_params
 from .engine import Engine, default_engine
 from .model import SPART, SpectralBands, load_optical_parameters, load_sensor_info
-from .params import (Angles, AtmosphericProperties, CanopyStructure, LeafBiology, SoilParameters, pack_params)
+from .params import (Angles, AtmosphericProperties, CanopyStructure, LeafBiology, SoilParameters,
+                     SoilParametersFromFile, pack_params)
 from .tables import SENSOR_NAMES, synthetic_fullspectrum_sensorinfo
 
 __all__ = [
-    "SPART", "SpectralBands", "LeafBiology", "SoilParameters", "CanopyStructure", "Angles",
+    "SPART", "SpectralBands", "LeafBiology", "SoilParameters", "SoilParametersFromFile", "CanopyStructure", "Angles",
     "AtmosphericProperties", "run_batch", "run_batch_params", "pack_batch", "pack_params",
     "row_as_dataframe", "Engine", "default_engine", "SpartError", "SENSOR_NAMES",
     "load_optical_parameters", "load_sensor_info", "synthetic_fullspectrum_sensorinfo",

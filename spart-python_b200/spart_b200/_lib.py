@@ -12,8 +12,9 @@ import os
 
 # SPART_B200_LIB lets kernel-tuning scripts load an alternative build of the same library
 LIB_PATH = Path(os.environ.get("SPART_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libspart_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_UNIFORM_GEOMETRY = 1
+FLAG_SOIL_SPECTRUM = 2
 NKERNELS = 3
 
 FP64 = 64
@@ -69,7 +70,8 @@ def load():
                                         c_void_p, c_void_p]
     lib.spart_forward_bands_host.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32,
                                              c_void_p]
-    lib.spart_forward_spectrum.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.spart_forward_spectrum.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                           c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]
     lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]

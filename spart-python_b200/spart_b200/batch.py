@@ -62,23 +62,28 @@ def pack_batch(leaf, soil, canopy, angles, atm, doy, device=None):
     return block.t().contiguous() if use_torch else np.ascontiguousarray(block.T)
 
 
-def run_batch_params(params, sensor, precision="fp64", device=None, out=None, uniform_geometry=False):
+def run_batch_params(params, sensor, precision="fp64", device=None, out=None, uniform_geometry=False,
+                     soil_spectrum=None):
     """params: [27, n] float64.  CUDA tensor in -> CUDA tensor [n, nb, 3] out (asynchronous on
     the current stream); NumPy array / CPU tensor in -> NumPy array out (copies pipelined in
     the C library).  uniform_geometry=True is the caller's promise that the angle rows 19..21 are
-    constant over the batch (one acquisition geometry); the result is identical, only faster."""
+    constant over the batch (one acquisition geometry); the result is identical, only faster.
+    soil_spectrum: dry-soil reflectance [2001] shared by the batch (the reference's
+    SoilParametersFromFile, bsm.py:155-226); the B / lat / lon rows are then ignored."""
     if isinstance(params, torch.Tensor) and params.is_cuda:
         return default_engine(params.device).forward_bands(params, sensor, out=out, precision=precision,
-                                                           uniform_geometry=uniform_geometry)
+                                                           uniform_geometry=uniform_geometry,
+                                                           soil_spectrum=soil_spectrum)
     return default_engine(device).forward_bands_host(params, sensor, out=out, precision=precision,
-                                                     uniform_geometry=uniform_geometry)
+                                                     uniform_geometry=uniform_geometry, soil_spectrum=soil_spectrum)
 
 
-def run_batch(leaf, soil, canopy, angles, atm, doy, sensor, precision="fp64", device=None, out=None):
+def run_batch(leaf, soil, canopy, angles, atm, doy, sensor, precision="fp64", device=None, out=None,
+              soil_spectrum=None):
     """Batched SPART forward run -> [n, nb, 3] ordered (R_TOC, R_TOA, L_TOA)."""
     shared = np.ndim(angles) == 1 or (hasattr(angles, "dim") and angles.dim() == 1)   # angles given as [3]
     return run_batch_params(pack_batch(leaf, soil, canopy, angles, atm, doy, device), sensor, precision, device, out,
-                            uniform_geometry=bool(shared))
+                            uniform_geometry=bool(shared), soil_spectrum=soil_spectrum)
 
 
 def row_as_dataframe(out_row, sensor, engine=None):

@@ -42,16 +42,29 @@ class Engine:
         self._lock = threading.Lock()
 
     # ---- contexts ------------------------------------------------------------------
-    def sensor(self, sensor):
-        """(ctx, SensorTables) for a shipped sensor name or a reference-style sensorinfo dict."""
-        key = sensor if isinstance(sensor, str) else ("custom", id(sensor))
+    def sensor(self, sensor, soil_spectrum=None):
+        """(ctx, SensorTables) for a shipped sensor name or a reference-style sensorinfo dict.
+        soil_spectrum: optional user dry-soil reflectance [2001] (SoilParametersFromFile); such a
+        context carries the spectrum as its first soil vector and must be run with
+        SPART_FLAG_SOIL_SPECTRUM."""
+        skey = sensor if isinstance(sensor, str) else ("custom", id(sensor))
+        soil = None
+        if soil_spectrum is not None:
+            soil = np.ascontiguousarray(np.asarray(soil_spectrum, dtype=np.float64).reshape(-1))
+            if soil.shape[0] != T.NWL:
+                raise ValueError("soil_spectrum must have 2001 values (400..2400 nm)")
+        key = (skey, None if soil is None else soil.tobytes())
         with self._lock:
             hit = self._ctx.get(key)
             if hit is not None:
                 return hit[0], hit[1]
             info = T.load_sensor_info(sensor) if isinstance(sensor, str) else sensor
             st = T.build_sensor(sensor if isinstance(sensor, str) else "custom", info, self._opt)
-            tabs = _lib.SpartTables(n_wl=T.NWL, lc=_lib.as_double_ptr(self._lc))
+            lc = self._lc
+            if soil is not None:
+                lc = self._lc.copy()
+                lc[11], lc[12], lc[13] = soil, 0.0, 0.0
+            tabs = _lib.SpartTables(n_wl=T.NWL, lc=_lib.as_double_ptr(lc))
             smac = np.ascontiguousarray(st.smac)
             cs = _lib.SpartSensor(n_bands=st.n_bands, wl_lo=_lib.as_int32_ptr(st.wl_lo),
                                   wl_hi=_lib.as_int32_ptr(st.wl_hi), wl_frac=_lib.as_double_ptr(st.wl_frac),
@@ -59,7 +72,7 @@ class Engine:
             handle = _lib.c_void_p()
             _lib.check(self.lib.spart_create(_lib.byref(tabs), _lib.byref(cs), 1, self.device.index,
                                              _lib.byref(handle)), "spart_create")
-            self._ctx[key] = (handle, st, (smac, sensor))
+            self._ctx[key] = (handle, st, (smac, sensor, lc))
             return handle, st
 
     def close(self):
@@ -84,11 +97,13 @@ class Engine:
             raise ValueError(f"params on {params.device}, engine on {self.device}")
         return params, params.shape[1], (params.stride(0) if params.shape[1] > 1 else max(params.shape[1], 1))
 
-    def forward_bands(self, params, sensor, out=None, precision="fp64", uniform_geometry=False):
+    def forward_bands(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
+                      soil_spectrum=None):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
         Asynchronous on the current torch stream.  uniform_geometry=True asserts that the three
-        angle rows are constant over the batch (SPART_FLAG_UNIFORM_GEOMETRY)."""
-        handle, st = self.sensor(sensor)
+        angle rows are constant over the batch (SPART_FLAG_UNIFORM_GEOMETRY).  soil_spectrum: dry
+        soil reflectance [2001] used instead of the B/lat/lon soil vectors."""
+        handle, st = self.sensor(sensor, soil_spectrum)
         params, n, ld = self._prep(params)
         if out is None:
             out = torch.empty((n, st.n_bands, NOUT), dtype=torch.float64, device=self.device)
@@ -97,7 +112,8 @@ class Engine:
             raise ValueError("out must be a contiguous CUDA float64 tensor [n, nb, 3]")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         prec = _PRECISION[precision]
-        flags = _lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0
+        flags = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
+            _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0)
         for s0 in range(0, n, MAX_SAMPLES_PER_CALL):
             m = min(MAX_SAMPLES_PER_CALL, n - s0)
             ws = torch.empty(self.lib.spart_workspace_bytes(handle, m) // 8, dtype=torch.float64, device=self.device)
@@ -106,17 +122,18 @@ class Engine:
                                                     stream), "spart_forward_bands")
         return out
 
-    def forward_spectrum(self, params, out=None):
+    def forward_spectrum(self, params, out=None, soil_spectrum=None):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, 9, 2162]: leaf refl, leaf tran,
         kChlrel, soil refl, soil refl dry, rso, rdo, rsd, rdd."""
-        handle, _ = self.sensor("Sentinel2A-MSI")       # any context carries the wavelength tables
+        handle, _ = self.sensor("Sentinel2A-MSI", soil_spectrum)   # any context carries the wavelength tables
         params, n, ld = self._prep(params)
         if out is None:
             out = torch.empty((n, NSPEC, NWL_S), dtype=torch.float64, device=self.device)
         ws = torch.empty(self.lib.spart_workspace_bytes(handle, n) // 8, dtype=torch.float64, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.spart_forward_spectrum(handle, params.data_ptr(), n, ld, ws.data_ptr(), out.data_ptr(),
-                                                   stream), "spart_forward_spectrum")
+        flags = _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0
+        _lib.check(self.lib.spart_forward_spectrum(handle, params.data_ptr(), n, ld, flags, ws.data_ptr(),
+                                                   out.data_ptr(), stream), "spart_forward_spectrum")
         return out
 
     def leafangles(self, ab):
@@ -130,10 +147,11 @@ class Engine:
         return out.cpu().numpy()
 
     # ---- host path -----------------------------------------------------------------
-    def forward_bands_host(self, params, sensor, out=None, precision="fp64", uniform_geometry=False):
+    def forward_bands_host(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
+                           soil_spectrum=None):
         """params: host float64 [27, n] (NumPy array or CPU tensor, ideally pinned) ->
         host float64 [n, nb, 3].  H2D, kernels and D2H are pipelined inside the C library."""
-        handle, st = self.sensor(sensor)
+        handle, st = self.sensor(sensor, soil_spectrum)
         p = params.numpy() if isinstance(params, torch.Tensor) else np.asarray(params)
         if p.dtype != np.float64 or p.ndim != 2 or p.shape[0] != NPAR or (p.shape[1] > 1 and p.strides[1] != 8):
             raise ValueError("params must be a host float64 array [27, n] with contiguous rows")
@@ -145,7 +163,8 @@ class Engine:
         if o.dtype != np.float64 or not o.flags.c_contiguous or o.shape != (n, st.n_bands, NOUT):
             raise ValueError("out must be a C-contiguous host float64 array [n, nb, 3]")
         with torch.cuda.device(self.device):
-            flags = _lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0
+            flags = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
+                _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0)
             _lib.check(self.lib.spart_forward_bands_host(handle, 0, p.ctypes.data, n, ld, _PRECISION[precision],
                                                          flags, o.ctypes.data), "spart_forward_bands_host")
         return out

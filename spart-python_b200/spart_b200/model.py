@@ -45,8 +45,6 @@ def load_sensor_info(sensor):
 
 class SPART:
     def __init__(self, soilpar, leafbio, canopy, atm, angles, sensor, DOY):
-        if getattr(soilpar, "rdry_set", False):
-            raise NotImplementedError("user-supplied dry soil spectra (SoilParametersFromFile) are not supported yet")
         self.soilpar = soilpar
         self.leafbio = leafbio
         self.canopy = canopy
@@ -61,6 +59,11 @@ class SPART:
 
     def _params(self):
         return pack_params(self.soilpar, self.leafbio, self.canopy, self.atm, self.angles, self.DOY)
+
+    def _soil_spectrum(self):
+        if getattr(self.soilpar, "rdry_set", False):
+            return np.asarray(self.soilpar.rdry, dtype=np.float64).reshape(-1)
+        return None
 
     def _sensor_key(self):
         # like the reference, a changed `sensor` attribute does not reload sensorinfo; a user
@@ -80,7 +83,7 @@ class SPART:
                   "therefore set to zero (Cdm = PROT + CBC)")
         key = self._sensor_key()
         p = self._params()
-        out = eng.forward_bands_host(p, key)[0]            # [nb, 3]
+        out = eng.forward_bands_host(p, key, soil_spectrum=self._soil_spectrum())[0]            # [nb, 3]
         self.R_TOC = out[:, 0][None, :].copy()
         self.R_TOA = out[:, 1][None, :].copy()
         self.L_TOA = out[:, 2][None, :].copy()
@@ -97,7 +100,7 @@ class SPART:
         if self._spec is None:
             eng = default_engine()
             p = torch.from_numpy(self._params()).to(eng.device)
-            self._spec = eng.forward_spectrum(p)[0].cpu().numpy()     # [9, 2162]
+            self._spec = eng.forward_spectrum(p, soil_spectrum=self._soil_spectrum())[0].cpu().numpy()     # [9, 2162]
         return self._spec
 
     @property

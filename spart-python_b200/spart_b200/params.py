@@ -59,6 +59,48 @@ class SoilParameters:
         return [self.B, self.lat, self.lon, self.SMp, self.SMC, self.film]
 
 
+class SoilParametersFromFile:
+    """Dry-soil reflectance supplied by the user: a JPL spectral-library text file
+    (https://speclib.jpl.nasa.gov/) or an array with the 2001 values for 400..2400 nm
+    (reference bsm.py:155-226).  SMp / SMC / film as in SoilParameters."""
+
+    def __init__(self, soil_file, SMp, SMC=None, film=None):
+        if SMC is None:
+            warnings.warn("BSM soil model: SMC not supplied, set to default of 25 %")
+            SMC = 25
+        self.SMC = SMC
+        if film is None:
+            warnings.warn("BSM soil model: water film optical thickness not supplied,")
+            warnings.warn("\t set to default of 0.0150 cm")
+            film = 0.0150
+        self.film = film
+        self.rdry = soil_file if isinstance(soil_file, np.ndarray) else self._load_jpl_soil_refl(soil_file)
+        self.SMp = SMp
+        self.rdry_set = True
+
+    @staticmethod
+    def _load_jpl_soil_refl(file_path):
+        """JPL file: 21 header lines, then tab-separated wavelength [um] / reflectance [% or
+        fraction] in descending wavelength order.  Returns [2001, 1] on the 1 nm grid; like the
+        reference, missing integer wavelengths are filled by pandas' positional linear
+        interpolation (bsm.py:201-226)."""
+        import pandas as pd
+        refl = pd.read_csv(file_path, sep="\t", skiprows=21, index_col=0, header=None)
+        refl.index = refl.index * 1000
+        if (refl.loc[:, 1] > 1).any():
+            refl = refl / 100
+        refl = refl.sort_index().loc[400:2401]       # label slice (the files list wavelengths descending)
+        wls = np.arange(400, 2401, 1)
+        missing = [wl for wl in wls if wl not in refl.index]
+        if missing:
+            refl = pd.concat([refl, pd.DataFrame({1: np.nan}, index=missing)])
+        refl = refl.sort_index().interpolate("linear")
+        return refl.loc[wls].to_numpy()
+
+    def as_row(self):
+        return [0.0, 0.0, 0.0, self.SMp, self.SMC, self.film]      # B, lat, lon are not used
+
+
 class CanopyStructure:
     """SAILH canopy: LAI, leaf-inclination parameters LIDFa / LIDFb, hot-spot parameter q.
     `nlayers`, `nlincl`, `nlazi` are the SAIL assumptions 60 / 13 / 36.  `lidf` (the

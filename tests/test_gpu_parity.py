@@ -220,6 +220,31 @@ def test_edge_cases(env):
     assert np.array_equal(one[0], gpu_bands(env, P, "LANDSAT8-OLI")[0])
 
 
+@pytest.mark.parametrize("name", ["soilfile_Sentinel2A", "soilfile_TerraAqua"])
+def test_user_soil_spectrum(env, name):
+    """SoilParametersFromFile: batched entry point and the SPART class against the reference."""
+    torch, sb, so = env
+    g = load_golden(f"{name}.npz")
+    P, sensor, rdry = g["params"], str(g["sensor"]), g["rdry"]
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    got = sb.run_batch_params(dev, sensor, soil_spectrum=rdry).cpu().numpy()
+    assert relerr(got, g["O2"]) < RTOL64
+    assert relerr(got, g["O1"]) < 5e-8
+    host = sb.run_batch_params(np.ascontiguousarray(P.T), sensor, soil_spectrum=rdry)
+    assert np.array_equal(host, got)
+    got32 = sb.run_batch_params(dev, sensor, soil_spectrum=rdry, precision="fp32").cpu().numpy()
+    assert np.percentile(np.abs(got32 - got) / np.abs(got), 99) < RTOL32
+    p = P[0]
+    spart = sb.SPART(sb.SoilParametersFromFile(rdry[:, None].copy(), p[12], p[13], p[14]),
+                     sb.LeafBiology(*p[0:9]), sb.CanopyStructure(*p[15:19]), sb.AtmosphericProperties(*p[22:26]),
+                     sb.Angles(*p[19:22]), sensor, int(p[26]))
+    res = spart.run(debug=True)
+    one = np.stack([res["R_TOC"].to_numpy(), res["R_TOA"].to_numpy(), res["L_TOA"].to_numpy()], axis=1)
+    assert relerr(one, g["O2"][0]) < RTOL64
+    assert np.allclose(spart.soilopt.refl_dry[:, 0], rdry, rtol=0, atol=0)
+    assert "rsoil" in res.columns
+
+
 def test_uniform_geometry_flag_is_only_an_optimisation(env):
     """SPART_FLAG_UNIFORM_GEOMETRY (shared sun/observer angles) must not change a single bit
     pattern beyond rounding: compare with the general path and with the oracle."""

@@ -94,6 +94,29 @@ def test_param_holders_mirror_reference():
     assert p.shape == (27, 1) and p[so.CDM, 0] == 10 and p[so.SMC, 0] == 25 and p[so.DOY, 0] == 100
 
 
+def test_soil_parameters_from_file(tmp_path):
+    """JPL spectral-library text format (bsm.py:201-226): 21 header lines, wavelength in
+    micrometres (descending), reflectance in percent."""
+    import spart_b200 as sb
+    wl_um = np.arange(2.5, 0.3995, -0.0005)                 # 0.5 nm steps, descending
+    refl_pct = 10 + 20 * (wl_um - 0.4)
+    f = tmp_path / "soil.txt"
+    with open(f, "w") as fh:
+        fh.write("\n".join(f"header {i}" for i in range(21)) + "\n")
+        for w, r in zip(wl_um, refl_pct):
+            fh.write(f"{w:.4f}\t{r:.6f}\n")
+    soil = sb.SoilParametersFromFile(str(f), 20, 25, 0.015)
+    assert soil.rdry_set and soil.rdry.shape == (2001, 1)
+    want = (10 + 20 * (np.arange(400, 2401) / 1000 - 0.4)) / 100
+    assert np.allclose(soil.rdry[:, 0], want, atol=1e-6)
+    with pytest.warns(UserWarning):
+        soil2 = sb.SoilParametersFromFile(want.copy(), 20)
+    assert soil2.SMC == 25 and soil2.film == 0.015 and soil2.rdry is not None
+    p = sb.pack_params(soil2, sb.LeafBiology(40, 0.01, 0.02, 0, 10, 10, 1.5), sb.CanopyStructure(3, -0.35, -0.15, 0.05),
+                       sb.AtmosphericProperties(0.3, 0.35, 1.4), sb.Angles(40, 0, 0), 100)
+    assert p[so.SMP, 0] == 20 and p[so.SOIL_B, 0] == 0
+
+
 def test_pack_batch_layout():
     import spart_b200 as sb
     P = so.synthetic_params(50, 3, seed=4)

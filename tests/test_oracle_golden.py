@@ -101,6 +101,15 @@ def test_oracle_cfg4_synthetic_sensor(optical):
     assert relerr(out, g["O1"]) < 1e-6
 
 
+@pytest.mark.parametrize("name", ["soilfile_Sentinel2A", "soilfile_TerraAqua"])
+def test_oracle_user_soil_spectrum(name, optical):
+    """SoilParametersFromFile path of the reference (bsm.py:42-43, 155-226)."""
+    g = load_golden(f"{name}.npz")
+    out = so.spart_bands(g["params"], str(g["sensor"]), optical, soil_rdry=g["rdry"])
+    assert relerr(out, g["O2"]) < 1e-12
+    assert relerr(out, g["O1"]) < 5e-8
+
+
 def test_closest_index_semantics():
     """get_closest_index (SPART.py:381-387): ties -> lower index, NaN -> 0."""
     wl_hi = np.arange(400, 2401)

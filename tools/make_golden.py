@@ -85,6 +85,21 @@ def run_one(task):
     return out, spec
 
 
+def run_soilfile(task):
+    """Reference run with SoilParametersFromFile(ndarray) (bsm.py:155-226)."""
+    import contextlib
+    import io
+    p, rdry, sensor, o2 = task
+    SPART = _ref_modules(o2)
+    from SPART.bsm import SoilParametersFromFile
+    _, leaf, canopy, atm, angles = _objects(SPART, p)
+    f = np.float64
+    soil = SoilParametersFromFile(rdry[:, None].copy(), f(p[12]), f(p[13]), f(p[14]))
+    with contextlib.redirect_stdout(io.StringIO()):
+        df = SPART.SPART(soil, leaf, canopy, atm, angles, sensor, int(p[26])).run()
+    return np.stack([df["R_TOC"].to_numpy(), df["R_TOA"].to_numpy(), df["L_TOA"].to_numpy()], axis=1)
+
+
 def run_prospect(task):
     import contextlib
     import io
@@ -134,6 +149,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jobs", type=int, default=8)
     ap.add_argument("--n", type=int, default=48, help="random samples per batch fixture")
+    ap.add_argument("--only", default=None, help="regenerate only this fixture group (e.g. soilfile)")
     args = ap.parse_args()
     import spart_oracle as so
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -148,6 +164,22 @@ def main():
                 for k in r[0][1]:
                     res[f"{tag}.{k}"] = np.stack([x[1][k] for x in r])
         return res
+
+    # 6. user-supplied dry-soil spectrum (SoilParametersFromFile)
+    if args.only in (None, "soilfile"):
+        wl = np.arange(400, 2401, dtype=np.float64)
+        rdry = 0.08 + 0.32 * (1 - np.exp(-(wl - 400) / 650)) - 0.05 * np.exp(-((wl - 1930) / 60) ** 2) \
+            - 0.03 * np.exp(-((wl - 1440) / 50) ** 2)
+        P = so.synthetic_params(16, 3, seed=61)
+        for sensor in ("Sentinel2A-MSI", "TerraAqua-MODIS"):
+            o1 = np.stack(pool.map(run_soilfile, [(p, rdry, sensor, False) for p in P]))
+            o2 = np.stack(pool.map(run_soilfile, [(p, rdry, sensor, True) for p in P]))
+            np.savez_compressed(GOLD / f"soilfile_{sensor.split('-')[0]}.npz", params=P, rdry=rdry,
+                                sensor=np.array(sensor), O1=o1, O2=o2)
+        print("soilfile done", flush=True)
+        if args.only:
+            pool.close()
+            return
 
     # 1. e2e: conftest defaults on all nine sensors + README quickstart + example script
     e2e = {}
