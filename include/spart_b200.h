@@ -141,6 +141,15 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params
 int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
                            int32_t flags, void* workspace_dev, double* out_dev, void* stream);
 
+/* Replaces SAILH(soil, leafopt, canopy, angles) on caller-supplied spectra (sailh.py:14-237).
+ * params_dev: [SPART_NPAR][ld]; only the canopy and angle rows 15..21 matter, the others must
+ * merely be finite.  soil_refl / leaf_refl / leaf_tran: double spectra of SPART_NWL_S (2162)
+ * wavelengths, sample s at offset s * spectra_stride (spectra_stride = 0: one spectrum shared by
+ * all samples).  out_dev: double [n][4][2162] = rso, rdo, rsd, rdd. */
+int spart_sailh(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
+                const double* soil_refl_dev, const double* leaf_refl_dev, const double* leaf_tran_dev,
+                int64_t spectra_stride, void* workspace_dev, double* out_dev, void* stream);
+
 /* Replaces CanopyStructure.__init__'s calculate_leafangles (sailh.py:340-398): the 13-class
  * leaf inclination distribution for n (LIDFa, LIDFb) pairs.  ab_dev: double [2][ld];
  * out_dev: double [n][13].  Needs no context. */

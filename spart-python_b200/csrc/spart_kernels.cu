@@ -472,6 +472,26 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   }
 }
 
+// SAILH on caller-supplied spectra (the reference's SAILH(soil, leafopt, canopy, angles),
+// sailh.py:14-237): thread = wavelength (coalesced reads of the three input spectra and writes
+// of the four outputs), blockIdx.y = sample; the sample's canopy record is a broadcast load.
+__global__ void __launch_bounds__(256)
+sailh_spectra_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+                     const double* __restrict__ rs, const double* __restrict__ rho, const double* __restrict__ tau,
+                     int64_t stride, int64_t s0, double* __restrict__ out) {
+  const int w = blockIdx.x * 256 + threadIdx.x;
+  const int64_t s = s0 + blockIdx.y;
+  if (w >= SPART_NWL_S || s >= n) return;
+  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+  double rso, rdo, rsd, rdd;
+  sailh_point(G, rho[s * stride + w], tau[s * stride + w], rs[s * stride + w], rso, rdo, rsd, rdd);
+  double* o = out + (size_t)s * 4 * SPART_NWL_S;
+  o[0 * SPART_NWL_S + w] = rso;
+  o[1 * SPART_NWL_S + w] = rdo;
+  o[2 * SPART_NWL_S + w] = rsd;
+  o[3 * SPART_NWL_S + w] = rdd;
+}
+
 // ---- FP32 mode (SPART_FP32) -----------------------------------------------------------------
 // Two kernels: per-sample geometry (leaf angles by safeguarded Newton, volume scattering,
 // hot-spot integrals, soil / atmosphere scalars) and the band kernel.  The per-sample record
@@ -1029,6 +1049,32 @@ int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_
   spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, out_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
+  return SPART_OK;
+}
+
+int spart_sailh(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld, const double* soil_refl_dev,
+                const double* leaf_refl_dev, const double* leaf_tran_dev, int64_t spectra_stride,
+                void* workspace_dev, double* out_dev, void* stream) {
+  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_sailh");
+  if (rc) return rc;
+  if (!soil_refl_dev || !leaf_refl_dev || !leaf_tran_dev) return fail(SPART_EINVAL, "spart_sailh: null spectrum%s");
+  if (spectra_stride != 0 && spectra_stride < SPART_NWL_S)
+    return fail(SPART_EINVAL, "spart_sailh: spectra_stride must be 0 (shared spectra) or >= 2162%s");
+  if (n == 0) return SPART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* rec = (double*)workspace_dev;
+  rc = launch_lidf(params_dev, n, ld, rec, st);
+  if (rc) return rc;
+  rc = launch_geometry(params_dev, n, ld, rec, 0, st);
+  if (rc) return rc;
+  for (int64_t s0 = 0; s0 < n; s0 += 65535) {
+    const unsigned ny = (unsigned)((n - s0 < 65535) ? (n - s0) : 65535);
+    dim3 grid((SPART_NWL_S + 255) / 256, ny);
+    sailh_spectra_kernel<<<grid, 256, 0, st>>>(params_dev, n, ld, rec, soil_refl_dev, leaf_refl_dev, leaf_tran_dev,
+                                               spectra_stride, s0, out_dev);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
   return SPART_OK;
 }
 

@@ -23,7 +23,7 @@ FP32 = 32
 EXPORTS = (
     "spart_abi_version", "spart_last_error", "spart_device_count", "spart_create", "spart_destroy",
     "spart_workspace_bytes", "spart_forward_bands", "spart_forward_bands_host", "spart_forward_spectrum",
-    "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
+    "spart_sailh", "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
 )
 
 
@@ -72,6 +72,8 @@ def load():
                                              c_void_p]
     lib.spart_forward_spectrum.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                            c_void_p]
+    lib.spart_sailh.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                c_void_p, c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]
     lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]

@@ -136,6 +136,29 @@ class Engine:
                                                    out.data_ptr(), stream), "spart_forward_spectrum")
         return out
 
+    def sailh(self, params, soil_refl, leaf_refl, leaf_tran, out=None):
+        """SAILH on caller-supplied spectra.  params: CUDA float64 [27, n] (canopy and angle rows
+        used); spectra: CUDA float64 [2162] (shared by all samples) or [n, 2162].
+        -> CUDA float64 [n, 4, 2162] = rso, rdo, rsd, rdd."""
+        handle, _ = self.sensor("Sentinel2A-MSI")
+        params, n, ld = self._prep(params)
+        specs = [soil_refl, leaf_refl, leaf_tran]
+        shared = all(x.dim() == 1 for x in specs)
+        for x in specs:
+            ok = x.is_cuda and x.dtype == torch.float64 and x.is_contiguous() and (
+                tuple(x.shape) == (NWL_S,) if shared else tuple(x.shape) == (n, NWL_S))
+            if not ok:
+                raise RuntimeError("Parameter leafopt.refl must be of len 2162 i.e. include thermal specturm "
+                                   "(CUDA float64, all three spectra [2162] or all [n, 2162])")
+        if out is None:
+            out = torch.empty((n, 4, NWL_S), dtype=torch.float64, device=self.device)
+        ws = torch.empty(self.lib.spart_workspace_bytes(handle, n) // 8, dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.spart_sailh(handle, params.data_ptr(), n, ld, soil_refl.data_ptr(), leaf_refl.data_ptr(),
+                                        leaf_tran.data_ptr(), 0 if shared else NWL_S, ws.data_ptr(), out.data_ptr(),
+                                        stream), "spart_sailh")
+        return out
+
     def leafangles(self, ab):
         """[n, 2] (LIDFa, LIDFb) host array -> [n, 13] lidf host array."""
         ab = np.ascontiguousarray(np.asarray(ab, dtype=np.float64).reshape(-1, 2).T)

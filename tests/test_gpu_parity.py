@@ -245,6 +245,60 @@ def test_user_soil_spectrum(env, name):
     assert "rsoil" in res.columns
 
 
+def test_prospect_stage_reference_grid(env):
+    """The reference's PROSPECT unit test (tests/unit/test_PROSPECT.py:17-28) on a subset of its grid
+    (build_PROSPECT_tests.py:38-50), through the reference-shaped PROSPECT_5D and the batched form."""
+    _, sb, _ = env
+    g = load_golden("prospect_grid.npz")
+    refl, tran, kchl = sb.prospect_batch(g["leaf7"])
+    got = np.stack([refl, tran, kchl], axis=1)
+    assert relerr(got, g["O2"]) < RTOL64
+    np.testing.assert_almost_equal(got, g["O1"], decimal=7)          # the reference's own criterion
+    r = sb.PROSPECT_5D(sb.LeafBiology(*g["leaf7"][0]), sb.load_optical_parameters())
+    assert r.refl.shape == (2001, 1) and np.array_equal(r.refl[:, 0], refl[0]) and np.array_equal(r.kChlrel[:, 0], kchl[0])
+
+
+def test_sailh_stage_reference_grid(env):
+    """The reference's SAILH unit test (tests/unit/test_SAILH.py:19-38) on a subset of its grid
+    (build_SAILH_tests.py:87-101) with the recorded default leaf / soil optics as inputs."""
+    _, sb, so = env
+    g = load_golden("sailh_grid.npz")
+    c7 = g["canopy_angles7"]
+    got = sb.sailh_batch(g["soil_refl"], g["leaf_refl"], g["leaf_tran"], c7[:, :4], c7[:, 4:7])
+    ok = np.isfinite(g["O1"])
+    assert (np.isfinite(got) == ok).all()
+    assert relerr(got[ok], g["O1"][ok]) < RTOL64
+    np.testing.assert_array_almost_equal(got[ok], g["O1"][ok], decimal=6)   # the reference's own criterion
+    # reference-shaped single call, per-sample spectra, and the length check of sailh.py:37-44
+    soil = sb.stages.SoilOptics(g["soil_refl"][:, None], None)
+    leaf = sb.stages.LeafOptics(g["leaf_refl"][:, None], g["leaf_tran"][:, None], None)
+    r = sb.SAILH(soil, leaf, sb.CanopyStructure(*c7[3, :4]), sb.Angles(*c7[3, 4:7]))
+    assert np.array_equal(r.rso[:, 0], got[3, 0]) and np.array_equal(r.rdd[:, 0], got[3, 3])
+    n = c7.shape[0]
+    per = sb.sailh_batch(np.repeat(g["soil_refl"][None], n, 0), np.repeat(g["leaf_refl"][None], n, 0),
+                         np.repeat(g["leaf_tran"][None], n, 0), c7[:, :4], c7[:, 4:7])
+    assert np.array_equal(per, got, equal_nan=True)
+    with pytest.raises(RuntimeError):
+        sb.SAILH(soil, sb.stages.LeafOptics(g["leaf_refl"][:2001, None], g["leaf_tran"][:2001, None], None),
+                 sb.CanopyStructure(3, -0.35, -0.15, 0.05), sb.Angles(40, 0, 0))
+
+
+def test_bsm_stage_and_padding(env):
+    _, sb, so = env
+    g = load_golden("spectra.npz")
+    P = g["params"]
+    wet, dry = sb.bsm_batch(P[:, 9:15])
+    assert relerr(wet, g["O2.soil_refl"][:, :2001]) < RTOL64 and relerr(dry, g["O2.soil_refl_dry"]) < RTOL64
+    soilopt = sb.BSM(sb.SoilParameters(*P[0, 9:15]))
+    leafbio = sb.LeafBiology(*P[0, 0:9])
+    leafopt = sb.PROSPECT_5D(leafbio)
+    soilopt = sb.set_soil_refl_trans_assumptions(soilopt)
+    leafopt = sb.set_leaf_refl_trans_assumptions(leafopt, leafbio)
+    assert soilopt.refl.shape == (2162, 1) and leafopt.tran.shape == (2162, 1) and leafopt.refl[-1, 0] == 0.01
+    r = sb.SAILH(soilopt, leafopt, sb.CanopyStructure(*P[0, 15:19]), sb.Angles(*P[0, 19:22]))
+    assert relerr(r.rso[:, 0], g["O2.rso"][0]) < RTOL64
+
+
 def test_uniform_geometry_flag_is_only_an_optimisation(env):
     """SPART_FLAG_UNIFORM_GEOMETRY (shared sun/observer angles) must not change a single bit
     pattern beyond rounding: compare with the general path and with the oracle."""
