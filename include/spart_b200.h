@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SPART_ABI_VERSION 3
+#define SPART_ABI_VERSION 4
 
 #define SPART_NPAR 27       /* rows of a parameter batch                                   */
 #define SPART_NWL 2001      /* 400..2400 nm, 1 nm (SpectralBands.wlP, SPART.py:303)        */
@@ -69,7 +69,11 @@ enum {
   /* the context was created with a user-supplied dry-soil spectrum in row 11 of SpartTables.lc
    * (rows 12, 13 zero): B / lat / lon are ignored and rdry = that spectrum, as with the reference's
    * SoilParametersFromFile (bsm.py:42-43, 155-226) */
-  SPART_FLAG_SOIL_SPECTRUM = 2
+  SPART_FLAG_SOIL_SPECTRUM = 2,
+  /* band values of the four canopy reflectances are SRF-weighted means over the band
+   * (calculate_spectral_convolution, SPART.py:358-396, applied to canopyopt) instead of the
+   * reference's np.interp sample at the band centre (SPART.py:216-223); SPART_FP64 only */
+  SPART_FLAG_SRF_BANDS = 4
 };
 
 typedef struct SpartCtx SpartCtx;
@@ -95,6 +99,14 @@ typedef struct {
   const double* wl_frac;   /* [n_bands] wl_smac - knot(wl_lo): np.interp weight (SPART.py:220-223) */
   const double* smac;      /* [SPART_NSMAC][n_bands] folded SMAC coefficients (smac.py:44-92)      */
   const double* conv_ea;   /* [n_bands] SRF-convolved Ea (SPART.py:358-396 applied to ETpar['Ea']) */
+  /* optional (all three NULL = not available): spectral response per band for
+   * SPART_FLAG_SRF_BANDS, already reduced to the 1-nm grid with the nearest-index rule of
+   * get_closest_index (SPART.py:381-387) and normalised by sum(p_srf): band b has srf_len[b]
+   * non-zero weights; its (wavelength index, weight) pairs follow those of band b-1 in
+   * srf_idx / srf_w */
+  const int32_t* srf_len;  /* [n_bands] */
+  const int32_t* srf_idx;  /* [sum(srf_len)] index into 400..2400 nm */
+  const double* srf_w;     /* [sum(srf_len)] */
 } SpartSensor;
 
 /* ABI version of the loaded library (== SPART_ABI_VERSION of the header it was built from). */

@@ -604,7 +604,18 @@ def canopy_spectra(params, opt=None, expint=_exp1, soil_rdry=None):
                 rso=rso, rdo=rdo, rsd=rsd, rdd=rdd)
 
 
-def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_canopy=False, soil_rdry=None):
+def srf_convolve(spectrum, opt, sensor):
+    """calculate_spectral_convolution (SPART.py:358-396) applied to [n, >=2001] spectra on the
+    400..2400 nm grid -> [n, nb]."""
+    idx = closest_index(sensor["wl_srf_smac"], opt["wl_Ea"])
+    p = sensor["p_srf_smac"]
+    rad = spectrum[:, idx]
+    with np.errstate(all="ignore"):
+        return np.sum(rad * p[None], axis=1) / np.sum(p, axis=0)[None, :]
+
+
+def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_canopy=False, soil_rdry=None,
+                band_mode="interp"):
     """SPART(...).run() (SPART.py:162-269) for a batch -> [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
 
     `sensor` is a sensor name or a sensorinfo dict.  faithful=True evaluates the whole
@@ -617,7 +628,11 @@ def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_c
     if isinstance(sensor, str):
         sensor = load_sensor(sensor)
     wl = sensor["wl_smac"].T[0]
-    if faithful:
+    if band_mode == "srf":     # extension: SRF-weighted band means of the canopy reflectances
+        cs = canopy_spectra(params, opt, expint=expint, soil_rdry=soil_rdry)
+        rv = {k: srf_convolve(cs[k], opt, sensor) for k in ("rso", "rdo", "rdd", "rsd")}
+        La = et_band_radiance(params[:, DOY], params[:, SZA], opt, sensor)
+    elif faithful:
         cs = canopy_spectra(params, opt, expint=expint, soil_rdry=soil_rdry)
         wlS = spectral_wlS()
         rv = {k: np.stack([np.interp(wl, wlS, row) for row in cs[k]]) for k in ("rso", "rdo", "rdd", "rsd")}

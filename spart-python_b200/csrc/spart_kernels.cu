@@ -87,6 +87,11 @@ struct SpartCtx {
   double* d_lc = nullptr;               // [LC_COUNT][SPART_NWL]
   std::vector<double*> d_band;          // per sensor [nb][BT_COUNT]
   std::vector<int> n_bands;
+  // optional SRF tables per sensor (band_mode "srf"): per band the number of non-zero weights and
+  // its offset into the concatenated (wavelength index, normalised weight) lists; nullptr when
+  // the sensor was created without them
+  std::vector<int32_t*> d_srf_idx, d_srf_len, d_srf_off;
+  std::vector<double*> d_srf_w;
   // host-buffer path: lazily created staging slots
   std::mutex mu;
   static const int kSlots = 3;
@@ -470,6 +475,72 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
     o[bi * SPART_NOUT + 1] = R_TOA;
     o[bi * SPART_NOUT + 2] = L_TOA;
   }
+}
+
+// Band kernel of the SRF mode (SPART_FLAG_SRF_BANDS): the four canopy reflectances of a band are
+// the spectral-response-weighted means over the band's support (calculate_spectral_convolution,
+// SPART.py:358-396, applied to canopyopt) instead of np.interp samples at the band centre.
+// blockIdx.x = band, blockIdx.y = sample tile, thread = sample; the (wavelength, weight) list is
+// walked in chunks of kSrfChunk entries whose constants and weights are staged in shared memory.
+constexpr int kSrfChunk = 32;
+
+__global__ void __launch_bounds__(kBandThreads, SPART_BAND_MINBLOCKS)
+band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+                const double* __restrict__ band_table, const double* __restrict__ lc_table,
+                const int32_t* __restrict__ srf_idx, const int32_t* __restrict__ srf_len,
+                const int32_t* __restrict__ srf_off, const double* __restrict__ srf_w, int nb,
+                double* __restrict__ out) {
+  __shared__ TauTable s_tau;
+  __shared__ double s_bt[BT_COUNT];
+  __shared__ double s_lc[kSrfChunk][LC_COUNT];
+  __shared__ double s_w[kSrfChunk];
+  const int b = blockIdx.x;
+  load_tau_table(&s_tau);
+  for (int i = threadIdx.x; i < BT_COUNT; i += blockDim.x) s_bt[i] = band_table[(size_t)b * BT_COUNT + i];
+  const int64_t s_raw = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
+  const bool valid = s_raw < n;
+  const int64_t s = valid ? s_raw : n - 1;
+  const LeafPar L = load_leaf(P, ld, s);
+  const SoilPar S = load_soil(P, ld, rec, n, s);
+  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+  const int len = srf_len[b];
+  const double* wts = srf_w + srf_off[b];
+  const int32_t* wix = srf_idx + srf_off[b];
+  double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
+  for (int c0 = 0; c0 < len; c0 += kSrfChunk) {
+    const int m = min(kSrfChunk, len - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * LC_COUNT; i += blockDim.x)
+      s_lc[i / LC_COUNT][i % LC_COUNT] = lc_table[(size_t)(i % LC_COUNT) * SPART_NWL + wix[c0 + i / LC_COUNT]];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_w[i] = wts[c0 + i];
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < m; ++j) {
+      const double wj = s_w[j];
+      double refl, tran, kchl, rwet, rdry, a0, a1, a2, a3;
+      prospect_point<false>(L, s_lc[j], &s_tau, refl, tran, kchl);
+      bsm_point(S, s_lc[j], rwet, rdry);
+      sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
+      rso = fma(wj, a0, rso);
+      rdo = fma(wj, a1, rdo);
+      rsd = fma(wj, a2, rsd);
+      rdd = fma(wj, a3, rdd);
+    }
+  }
+  if (!valid) return;
+  AtmSample A;
+  A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
+  A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s]; A.lpeq = rec[R_LPEQ * n + s];
+  A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
+  A.taup550 = P[P_AOT * ld + s];
+  A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
+  A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
+  double R_TOC, R_TOA, L_TOA;
+  smac_toa_band(A, &s_bt[BT_SMAC], s_bt[BT_CONVEA], rec[R_ETSCALE * n + s], rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
+  double* o = out + ((size_t)s * nb + b) * SPART_NOUT;
+  o[0] = R_TOC;
+  o[1] = R_TOA;
+  o[2] = L_TOA;
 }
 
 // SAILH on caller-supplied spectra (the reference's SAILH(soil, leafopt, canopy, angles),
@@ -894,6 +965,32 @@ int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t 
     CUDA_TRY(cudaMemcpy(d, bt.data(), bt.size() * sizeof(double), cudaMemcpyHostToDevice));
     ctx->d_band.push_back(d);
     ctx->n_bands.push_back(S.n_bands);
+    int32_t *d_idx = nullptr, *d_len = nullptr, *d_off = nullptr;
+    double* d_w = nullptr;
+    if (S.srf_idx && S.srf_len && S.srf_w) {
+      std::vector<int32_t> off(S.n_bands);
+      int64_t total = 0;
+      for (int b = 0; b < S.n_bands; ++b) {
+        if (S.srf_len[b] < 0) return fail(SPART_EINVAL, "spart_create: negative SRF length%s");
+        off[b] = (int32_t)total;
+        total += S.srf_len[b];
+      }
+      for (int64_t i = 0; i < total; ++i)
+        if (S.srf_idx[i] < 0 || S.srf_idx[i] >= SPART_NWL)
+          return fail(SPART_EINVAL, "spart_create: SRF wavelength index outside 400..2400 nm%s");
+      CUDA_TRY(cudaMalloc(&d_idx, sizeof(int32_t) * (total > 0 ? total : 1)));
+      CUDA_TRY(cudaMalloc(&d_len, sizeof(int32_t) * S.n_bands));
+      CUDA_TRY(cudaMalloc(&d_off, sizeof(int32_t) * S.n_bands));
+      CUDA_TRY(cudaMalloc(&d_w, sizeof(double) * (total > 0 ? total : 1)));
+      CUDA_TRY(cudaMemcpy(d_idx, S.srf_idx, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(d_len, S.srf_len, sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(d_off, off.data(), sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(d_w, S.srf_w, sizeof(double) * total, cudaMemcpyHostToDevice));
+    }
+    ctx->d_srf_idx.push_back(d_idx);
+    ctx->d_srf_len.push_back(d_len);
+    ctx->d_srf_off.push_back(d_off);
+    ctx->d_srf_w.push_back(d_w);
   }
   *out = ctx;
   return SPART_OK;
@@ -912,6 +1009,10 @@ int spart_destroy(SpartCtx* ctx) {
   for (auto& pe : ctx->prof_pending) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
   for (auto& pe : ctx->prof_free) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
   for (double* d : ctx->d_band) cudaFree(d);
+  for (auto* d : ctx->d_srf_idx) if (d) cudaFree(d);
+  for (auto* d : ctx->d_srf_len) if (d) cudaFree(d);
+  for (auto* d : ctx->d_srf_off) if (d) cudaFree(d);
+  for (auto* d : ctx->d_srf_w) if (d) cudaFree(d);
   if (ctx->d_lc) cudaFree(ctx->d_lc);
   delete ctx;
   return SPART_OK;
@@ -958,6 +1059,11 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
   if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "spart_forward_bands: unknown sensor%s");
   if (precision != SPART_FP64 && precision != SPART_FP32)
     return fail(SPART_EINVAL, "spart_forward_bands: precision must be SPART_FP64 or SPART_FP32%s");
+  if (flags & SPART_FLAG_SRF_BANDS) {
+    if (precision != SPART_FP64) return fail(SPART_EINVAL, "spart_forward_bands: SRF band mode needs SPART_FP64%s");
+    if (!ctx->d_srf_w[sensor])
+      return fail(SPART_EINVAL, "spart_forward_bands: this sensor was created without SRF tables%s");
+  }
   if (n == 0) return SPART_OK;
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
@@ -985,7 +1091,14 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
     rc = launch_geometry(params_dev, n, ld, rec, flags, st);
     if (rc) return rc;
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
-    band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+    if (flags & SPART_FLAG_SRF_BANDS) {
+      dim3 sgrid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
+      band_kernel_srf<<<sgrid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], ctx->d_lc,
+                                                      ctx->d_srf_idx[sensor], ctx->d_srf_len[sensor],
+                                                      ctx->d_srf_off[sensor], ctx->d_srf_w[sensor], nb, out_dev);
+    } else {
+      band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+    }
   } else {   // SPART_FP32: the leaf angles are solved inside the geometry kernel
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
     const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);

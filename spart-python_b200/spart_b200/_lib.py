@@ -12,9 +12,10 @@ import os
 
 # SPART_B200_LIB lets kernel-tuning scripts load an alternative build of the same library
 LIB_PATH = Path(os.environ.get("SPART_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libspart_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_UNIFORM_GEOMETRY = 1
 FLAG_SOIL_SPECTRUM = 2
+FLAG_SRF_BANDS = 4
 NKERNELS = 3
 
 FP64 = 64
@@ -43,6 +44,9 @@ class SpartSensor(Structure):
         ("wl_frac", POINTER(c_double)),
         ("smac", POINTER(c_double)),
         ("conv_ea", POINTER(c_double)),
+        ("srf_len", POINTER(c_int32)),
+        ("srf_idx", POINTER(c_int32)),
+        ("srf_w", POINTER(c_double)),
     ]
 
 

@@ -63,27 +63,30 @@ def pack_batch(leaf, soil, canopy, angles, atm, doy, device=None):
 
 
 def run_batch_params(params, sensor, precision="fp64", device=None, out=None, uniform_geometry=False,
-                     soil_spectrum=None):
+                     soil_spectrum=None, band_mode="interp"):
     """params: [27, n] float64.  CUDA tensor in -> CUDA tensor [n, nb, 3] out (asynchronous on
     the current stream); NumPy array / CPU tensor in -> NumPy array out (copies pipelined in
     the C library).  uniform_geometry=True is the caller's promise that the angle rows 19..21 are
     constant over the batch (one acquisition geometry); the result is identical, only faster.
     soil_spectrum: dry-soil reflectance [2001] shared by the batch (the reference's
-    SoilParametersFromFile, bsm.py:155-226); the B / lat / lon rows are then ignored."""
+    SoilParametersFromFile, bsm.py:155-226); the B / lat / lon rows are then ignored.
+    band_mode="srf" replaces the reference's np.interp band sampling of the canopy reflectances by
+    the sensor's spectral-response-weighted band means (FP64 only)."""
     if isinstance(params, torch.Tensor) and params.is_cuda:
         return default_engine(params.device).forward_bands(params, sensor, out=out, precision=precision,
                                                            uniform_geometry=uniform_geometry,
-                                                           soil_spectrum=soil_spectrum)
+                                                           soil_spectrum=soil_spectrum, band_mode=band_mode)
     return default_engine(device).forward_bands_host(params, sensor, out=out, precision=precision,
-                                                     uniform_geometry=uniform_geometry, soil_spectrum=soil_spectrum)
+                                                     uniform_geometry=uniform_geometry, soil_spectrum=soil_spectrum,
+                                                     band_mode=band_mode)
 
 
 def run_batch(leaf, soil, canopy, angles, atm, doy, sensor, precision="fp64", device=None, out=None,
-              soil_spectrum=None):
+              soil_spectrum=None, band_mode="interp"):
     """Batched SPART forward run -> [n, nb, 3] ordered (R_TOC, R_TOA, L_TOA)."""
     shared = np.ndim(angles) == 1 or (hasattr(angles, "dim") and angles.dim() == 1)   # angles given as [3]
     return run_batch_params(pack_batch(leaf, soil, canopy, angles, atm, doy, device), sensor, precision, device, out,
-                            uniform_geometry=bool(shared), soil_spectrum=soil_spectrum)
+                            uniform_geometry=bool(shared), soil_spectrum=soil_spectrum, band_mode=band_mode)
 
 
 def row_as_dataframe(out_row, sensor, engine=None):

@@ -68,7 +68,9 @@ class Engine:
             smac = np.ascontiguousarray(st.smac)
             cs = _lib.SpartSensor(n_bands=st.n_bands, wl_lo=_lib.as_int32_ptr(st.wl_lo),
                                   wl_hi=_lib.as_int32_ptr(st.wl_hi), wl_frac=_lib.as_double_ptr(st.wl_frac),
-                                  smac=_lib.as_double_ptr(smac), conv_ea=_lib.as_double_ptr(st.conv_ea))
+                                  smac=_lib.as_double_ptr(smac), conv_ea=_lib.as_double_ptr(st.conv_ea),
+                                  srf_len=_lib.as_int32_ptr(st.srf_len), srf_idx=_lib.as_int32_ptr(st.srf_idx),
+                                  srf_w=_lib.as_double_ptr(st.srf_w))
             handle = _lib.c_void_p()
             _lib.check(self.lib.spart_create(_lib.byref(tabs), _lib.byref(cs), 1, self.device.index,
                                              _lib.byref(handle)), "spart_create")
@@ -98,11 +100,14 @@ class Engine:
         return params, params.shape[1], (params.stride(0) if params.shape[1] > 1 else max(params.shape[1], 1))
 
     def forward_bands(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
-                      soil_spectrum=None):
+                      soil_spectrum=None, band_mode="interp"):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
         Asynchronous on the current torch stream.  uniform_geometry=True asserts that the three
         angle rows are constant over the batch (SPART_FLAG_UNIFORM_GEOMETRY).  soil_spectrum: dry
-        soil reflectance [2001] used instead of the B/lat/lon soil vectors."""
+        soil reflectance [2001] used instead of the B/lat/lon soil vectors.  band_mode: "interp"
+        (the reference: np.interp at the band centre) or "srf" (SRF-weighted band means)."""
+        if band_mode not in ("interp", "srf"):
+            raise ValueError("band_mode must be 'interp' or 'srf'")
         handle, st = self.sensor(sensor, soil_spectrum)
         params, n, ld = self._prep(params)
         if out is None:
@@ -113,7 +118,8 @@ class Engine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         prec = _PRECISION[precision]
         flags = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
-            _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0)
+            _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0) | (
+            _lib.FLAG_SRF_BANDS if band_mode == "srf" else 0)
         for s0 in range(0, n, MAX_SAMPLES_PER_CALL):
             m = min(MAX_SAMPLES_PER_CALL, n - s0)
             ws = torch.empty(self.lib.spart_workspace_bytes(handle, m) // 8, dtype=torch.float64, device=self.device)
@@ -171,7 +177,7 @@ class Engine:
 
     # ---- host path -----------------------------------------------------------------
     def forward_bands_host(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
-                           soil_spectrum=None):
+                           soil_spectrum=None, band_mode="interp"):
         """params: host float64 [27, n] (NumPy array or CPU tensor, ideally pinned) ->
         host float64 [n, nb, 3].  H2D, kernels and D2H are pipelined inside the C library."""
         handle, st = self.sensor(sensor, soil_spectrum)
@@ -186,8 +192,11 @@ class Engine:
         if o.dtype != np.float64 or not o.flags.c_contiguous or o.shape != (n, st.n_bands, NOUT):
             raise ValueError("out must be a C-contiguous host float64 array [n, nb, 3]")
         with torch.cuda.device(self.device):
+            if band_mode not in ("interp", "srf"):
+                raise ValueError("band_mode must be 'interp' or 'srf'")
             flags = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
-                _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0)
+                _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0) | (
+                _lib.FLAG_SRF_BANDS if band_mode == "srf" else 0)
             _lib.check(self.lib.spart_forward_bands_host(handle, 0, p.ctypes.data, n, ld, _PRECISION[precision],
                                                          flags, o.ctypes.data), "spart_forward_bands_host")
         return out

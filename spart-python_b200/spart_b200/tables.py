@@ -126,6 +126,9 @@ class SensorTables:
     conv_ea: np.ndarray        # [nb] float64
     srf_index: np.ndarray      # [n_srf, nb] nearest 1-nm index of every SRF sample
     srf_weight: np.ndarray     # [n_srf, nb]
+    srf_len: np.ndarray        # [nb] int32 number of non-zero SRF weights on the 1-nm grid
+    srf_idx: np.ndarray        # [sum(srf_len)] int32 wavelength indices
+    srf_w: np.ndarray          # [sum(srf_len)] normalised weights
 
 
 def fold_smac(coef):
@@ -162,17 +165,35 @@ def build_sensor(name, info, opt=None):
     nb = x.shape[0]
     if np.any(x < 400) or np.any(x > 2400):
         raise ValueError(f"sensor {name!r}: band centres must lie in 400..2400 nm")
-    lo = np.floor(x).astype(np.int64) - 400
-    frac = x - (lo + 400)
-    hi = np.where(frac == 0, lo, lo + 1)
+    klo = np.floor(x).astype(np.int64) - 400
+    frac = x - (klo + 400)
+    khi = np.where(frac == 0, klo, klo + 1)
     idx = nearest_index(info["wl_srf_smac"], opt["wl_Ea"])
     p = np.asarray(info["p_srf_smac"], dtype=np.float64)
     ea = np.asarray(opt["Ea"], dtype=np.float64).reshape(-1)
     with np.errstate(all="ignore"):
         conv_ea = np.sum(ea[idx] * p, axis=0) / np.sum(p, axis=0)
+    # dense SRF weights on the 1-nm grid: W[l, b] = sum of p over the SRF samples whose nearest
+    # wavelength is l, divided by sum(p) (what calculate_spectral_convolution evaluates)
+    W = np.zeros((NWL, nb))
+    with np.errstate(all="ignore"):
+        pn = p / np.sum(p, axis=0)[None, :]
+    for b in range(nb):
+        np.add.at(W[:, b], idx[:, b], np.nan_to_num(pn[:, b], nan=0.0))
+    W[np.abs(W) < 1e-200] = 0.0      # uninitialised ~1e-310 padding weights of the Sentinel-2 tables: no effect
+    ln = np.zeros(nb, dtype=np.int32)
+    ichunks, wchunks = [], []
+    for b in range(nb):
+        nz = np.nonzero(W[:, b])[0]
+        ln[b] = nz.size
+        ichunks.append(nz.astype(np.int32))
+        wchunks.append(W[nz, b])
+    srf_idx = np.ascontiguousarray(np.concatenate(ichunks)) if ichunks else np.zeros(0, dtype=np.int32)
+    srf_w = np.ascontiguousarray(np.concatenate(wchunks)) if wchunks else np.zeros(0)
     return SensorTables(
+        srf_len=ln, srf_idx=srf_idx, srf_w=srf_w,
         name=name, n_bands=nb, wl_smac=wl_smac, band_id=[str(b) for b in info["band_id_smac"]],
-        wl_lo=lo.astype(np.int32), wl_hi=hi.astype(np.int32), wl_frac=np.ascontiguousarray(frac),
+        wl_lo=klo.astype(np.int32), wl_hi=khi.astype(np.int32), wl_frac=np.ascontiguousarray(frac),
         smac=fold_smac(info["SMAC_coef"]), conv_ea=np.ascontiguousarray(conv_ea),
         srf_index=idx, srf_weight=p,
     )

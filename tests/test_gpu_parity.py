@@ -345,3 +345,22 @@ def test_large_batch_properties(env):
     idx = np.random.default_rng(0).choice(n, 256, replace=False)
     want = so.spart_bands(P[idx], "Sentinel2A-MSI")
     assert relerr(a[torch.from_numpy(idx).cuda()].cpu().numpy(), want) < RTOL64
+
+
+@pytest.mark.parametrize("sensor,cfg", [("Sentinel2A-MSI", 2), ("LANDSAT8-OLI", 3), ("TerraAqua-MODIS", 3)])
+def test_srf_band_mode(env, sensor, cfg):
+    """band_mode="srf": SRF-weighted band means of the canopy reflectances
+    (calculate_spectral_convolution, SPART.py:358-396, applied to canopyopt), then the same
+    SMAC / TOC->TOA algebra.  Oracle = that function on the oracle's full spectra."""
+    torch, sb, so = env
+    P = so.synthetic_params(300, cfg, seed=3000 + cfg)
+    want = so.spart_bands(P, sensor, band_mode="srf")
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    got = sb.run_batch_params(dev, sensor, band_mode="srf").cpu().numpy()
+    assert relerr(got, want) < RTOL64
+    interp = sb.run_batch_params(dev, sensor).cpu().numpy()
+    assert relerr(got, interp) > 1e-4        # it really is a different band definition
+    host = sb.run_batch_params(np.ascontiguousarray(P.T), sensor, band_mode="srf")
+    assert np.array_equal(host, got)
+    with pytest.raises(sb.SpartError):
+        sb.run_batch_params(dev, sensor, band_mode="srf", precision="fp32")
