@@ -73,7 +73,12 @@ enum {
   /* band values of the four canopy reflectances are SRF-weighted means over the band
    * (calculate_spectral_convolution, SPART.py:358-396, applied to canopyopt) instead of the
    * reference's np.interp sample at the band centre (SPART.py:216-223); SPART_FP64 only */
-  SPART_FLAG_SRF_BANDS = 4
+  SPART_FLAG_SRF_BANDS = 4,
+  /* the workspace still holds the per-sample record of a previous spart_forward_bands call for
+   * the same params / n / precision / soil flag (any sensor): skip the per-sample kernels and run
+   * only the band kernel.  This is how one batch is evaluated for several sensors (e.g.
+   * Sentinel-2A and -2B) while paying for the sensor-independent work once. */
+  SPART_FLAG_REUSE_RECORD = 8
 };
 
 typedef struct SpartCtx SpartCtx;

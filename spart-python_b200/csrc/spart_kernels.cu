@@ -1083,13 +1083,18 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
   }
   const int nb = ctx->n_bands[sensor];
   dim3 grid((unsigned)((nb + kBandChunk - 1) / kBandChunk), (unsigned)((n + kBandThreads - 1) / kBandThreads));
+  const bool reuse = (flags & SPART_FLAG_REUSE_RECORD) != 0;   // workspace already holds this batch's record
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
   if (precision == SPART_FP64) {
-    rc = launch_lidf(params_dev, n, ld, rec, st);
-    if (rc) return rc;
+    if (!reuse) {
+      rc = launch_lidf(params_dev, n, ld, rec, st);
+      if (rc) return rc;
+    }
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
-    rc = launch_geometry(params_dev, n, ld, rec, flags, st);
-    if (rc) return rc;
+    if (!reuse) {
+      rc = launch_geometry(params_dev, n, ld, rec, flags, st);
+      if (rc) return rc;
+    }
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
     if (flags & SPART_FLAG_SRF_BANDS) {
       dim3 sgrid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
@@ -1101,10 +1106,12 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
     }
   } else {   // SPART_FP32: the leaf angles are solved inside the geometry kernel
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
-    const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
-    geometry_kernel_f32<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, (float*)rec, flags);
-    ++g_launches;
-    CUDA_TRY(cudaGetLastError());
+    if (!reuse) {
+      const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+      geometry_kernel_f32<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, (float*)rec, flags);
+      ++g_launches;
+      CUDA_TRY(cudaGetLastError());
+    }
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
     band_kernel_f32<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, (const float*)rec, ctx->d_band[sensor], nb,
                                                     out_dev);

@@ -16,6 +16,7 @@ ABI_VERSION = 4
 FLAG_UNIFORM_GEOMETRY = 1
 FLAG_SOIL_SPECTRUM = 2
 FLAG_SRF_BANDS = 4
+FLAG_REUSE_RECORD = 8
 NKERNELS = 3
 
 FP64 = 64

@@ -72,6 +72,18 @@ def run_batch_params(params, sensor, precision="fp64", device=None, out=None, un
     SoilParametersFromFile, bsm.py:155-226); the B / lat / lon rows are then ignored.
     band_mode="srf" replaces the reference's np.interp band sampling of the canopy reflectances by
     the sensor's spectral-response-weighted band means (FP64 only)."""
+    if isinstance(sensor, (list, tuple)):      # several sensors on one batch (e.g. Sentinel-2A + -2B)
+        if not (isinstance(params, torch.Tensor) and params.is_cuda):
+            eng = default_engine(device)
+            dev_params = torch.as_tensor(np.ascontiguousarray(params) if not isinstance(params, torch.Tensor)
+                                         else params).to(eng.device)
+            outs = eng.forward_bands_multi(dev_params, list(sensor), precision=precision,
+                                           uniform_geometry=uniform_geometry, soil_spectrum=soil_spectrum,
+                                           band_mode=band_mode)
+            return [o.cpu().numpy() for o in outs]
+        return default_engine(params.device).forward_bands_multi(params, list(sensor), outs=out, precision=precision,
+                                                                 uniform_geometry=uniform_geometry,
+                                                                 soil_spectrum=soil_spectrum, band_mode=band_mode)
     if isinstance(params, torch.Tensor) and params.is_cuda:
         return default_engine(params.device).forward_bands(params, sensor, out=out, precision=precision,
                                                            uniform_geometry=uniform_geometry,

@@ -128,6 +128,28 @@ class Engine:
                                                     stream), "spart_forward_bands")
         return out
 
+    def forward_bands_multi(self, params, sensors, outs=None, precision="fp64", uniform_geometry=False,
+                            soil_spectrum=None, band_mode="interp"):
+        """One batch evaluated for several sensors: the sensor-independent per-sample kernels run
+        once and every further sensor only runs the band kernel (SPART_FLAG_REUSE_RECORD).
+        Returns a list of CUDA float64 [n, nb_i, 3] tensors."""
+        params, n, ld = self._prep(params)
+        if n > MAX_SAMPLES_PER_CALL:
+            raise ValueError(f"forward_bands_multi handles at most {MAX_SAMPLES_PER_CALL} samples per call")
+        ctxs = [self.sensor(s, soil_spectrum) for s in sensors]
+        if outs is None:
+            outs = [torch.empty((n, st.n_bands, NOUT), dtype=torch.float64, device=self.device) for _, st in ctxs]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        base = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
+            _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0) | (
+            _lib.FLAG_SRF_BANDS if band_mode == "srf" else 0)
+        ws = torch.empty(self.lib.spart_workspace_bytes(ctxs[0][0], n) // 8, dtype=torch.float64, device=self.device)
+        for i, ((handle, st), out) in enumerate(zip(ctxs, outs)):
+            flags = base | (_lib.FLAG_REUSE_RECORD if i > 0 else 0)
+            _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr(), n, ld, _PRECISION[precision], flags,
+                                                    ws.data_ptr(), out.data_ptr(), stream), "spart_forward_bands")
+        return outs
+
     def forward_spectrum(self, params, out=None, soil_spectrum=None):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, 9, 2162]: leaf refl, leaf tran,
         kChlrel, soil refl, soil refl dry, rso, rdo, rsd, rdd."""

@@ -364,3 +364,17 @@ def test_srf_band_mode(env, sensor, cfg):
     assert np.array_equal(host, got)
     with pytest.raises(sb.SpartError):
         sb.run_batch_params(dev, sensor, band_mode="srf", precision="fp32")
+
+
+def test_multi_sensor_shares_the_per_sample_work(env):
+    """Config 5 of BASELINE.json (Sentinel-2A + -2B on one batch): the second sensor reuses the
+    per-sample record (SPART_FLAG_REUSE_RECORD) and must give exactly the single-sensor result."""
+    torch, sb, so = env
+    P = so.synthetic_params(5000, 5, seed=50)
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    for prec in ("fp64", "fp32"):
+        a, b = sb.run_batch_params(dev, ["Sentinel2A-MSI", "Sentinel2B-MSI"], precision=prec, uniform_geometry=True)
+        assert torch.equal(a, sb.run_batch_params(dev, "Sentinel2A-MSI", precision=prec, uniform_geometry=True))
+        assert torch.equal(b, sb.run_batch_params(dev, "Sentinel2B-MSI", precision=prec, uniform_geometry=True))
+    ha, hb = sb.run_batch_params(np.ascontiguousarray(P.T), ["Sentinel2A-MSI", "Sentinel2B-MSI"])
+    assert relerr(hb, so.spart_bands(P, "Sentinel2B-MSI")) < RTOL64 and ha.shape == (5000, 13, 3)
