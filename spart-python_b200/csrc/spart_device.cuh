@@ -172,6 +172,22 @@ __device__ __forceinline__ double exp_fast(double x) {
   return (p * s1) * s2;
 }
 
+// exp with the argument clamped to [-700, 700] by NaN-preserving selects and one-step scaling:
+// results below e^-700 ~ 1e-304 come out as 1e-304 instead of 0 / subnormal and overflow
+// saturates at e^700; used where such values are physically irrelevant (transmittances,
+// Poisson weights).  NaN in -> NaN out.
+__device__ __forceinline__ double exp_clamp(double x) {
+#if !SPART_FAST_EXP
+  return exp(x);
+#endif
+  double xc = x;
+  xc = (x < -700.0) ? -700.0 : xc;
+  xc = (x > 700.0) ? 700.0 : xc;
+  int k;
+  const double p = exp_core(xc, k);
+  return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
 // exp for call sites that guarantee |x| <= 700 for finite inputs (NaN still propagates).
 __device__ __forceinline__ double exp_bounded(double x) {
 #if !SPART_FAST_EXP
@@ -343,14 +359,14 @@ __device__ __forceinline__ void bsm_point(const SoilPar& S, const double* lc, do
   if (S.mu > 0.0) {
     const double rbac = 1.0 - (1.0 - rdry) * (rdry * lc[LC_SOILC1] + 1.0 - rdry);
     const double p = lc[LC_SOILP], Rw = lc[LC_SOILRW];
-    const double tw1 = exp_fast(-2.0 * lc[LC_KW] * S.film);
+    const double tw1 = exp_clamp(-2.0 * lc[LC_KW] * S.film);
     double fk = S.emu;           // Poisson weight k = 0
     double acc = rdry * fk;
     double tw = 1.0;
     const double g = (1.0 - Rw) * (1.0 - p);
 #pragma unroll
     for (int k = 1; k <= 6; ++k) {
-      tw *= tw1;                 // exp_fast(-2 kw film k)
+      tw *= tw1;                 // exp_clamp(-2 kw film k)
       fk = fk * S.mu * (1.0 / (double)k);
       const double x = tw * rbac;
       acc += (Rw + g * x / (1.0 - p * x)) * fk;
@@ -391,7 +407,7 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
   const double rinf = (a - m) / sigb;
   const double rinf2 = rinf * rinf;
 
-  const double e1 = exp_fast(-m * LAI);
+  const double e1 = exp_clamp(-m * LAI);
   const double e2 = e1 * e1;
   const double tau_ss = G.tau_ss, tau_oo = G.tau_oo;
   const double inv_km = 1.0 / (k + m), inv_Km = 1.0 / (K + m);
@@ -549,14 +565,14 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
 
   // gaseous transmission, smac.py:105-119
   double gsum = 0.0;
-  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp_fast(c[SM_NO3] * S.lo3);
-  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp_fast(c[SM_NH2O] * S.lh2o);
-  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp_fast(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
-  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp_fast(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
-  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp_fast(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
-  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp_fast(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
-  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp_fast(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
-  const double tg = exp_fast(gsum);
+  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp_clamp(c[SM_NO3] * S.lo3);
+  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp_clamp(c[SM_NH2O] * S.lh2o);
+  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp_clamp(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
+  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp_clamp(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
+  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp_clamp(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
+  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp_clamp(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
+  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp_clamp(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
+  const double tg = exp_clamp(gsum);
 
   const double s = c[SM_A0S] * Peq + c[SM_A3S] + c[SM_A1S] * taup550 + c[SM_A2S] * taup550 * taup550;
   const double tnum = c[SM_A2T] * Peq + c[SM_A3T];
@@ -582,13 +598,13 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double f = -0.25 * h3 * us2 * wo * inv_q;
   const double dp = e * inv_us * (1.0 / 3.0) + us * f;
   const double d = e + f;
-  const double eak = exp_fast(ak * taup);
+  const double eak = exp_clamp(ak * taup);
   const double emak = 1.0 / eak;
   const double inv_delta = 1.0 / (eak * c[SM_OPB2] - emak * c[SM_OMB2]);
   const double ss = us * inv_q;
   const double q1 = 2.0 + 3.0 * us + h3 * us * (1.0 + 2.0 * us);
   const double q2 = 2.0 - 3.0 * us - h3 * us * (1.0 - 2.0 * us);
-  const double Eu = exp_fast(-taup * inv_us), Ev = exp_fast(-taup * inv_uv);
+  const double Eu = exp_clamp(-taup * inv_us), Ev = exp_clamp(-taup * inv_uv);
   const double q3 = q2 * Eu;
   const double wsd = c[SM_WW] * ss * inv_delta;
   const double c1 = wsd * (q1 * eak * opb + q3 * omb);
@@ -601,7 +617,7 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double y = c2 - g3uv * cp2;
   const double aa1 = uv / (1.0 + ak * uv);
   const double aa2 = uv / (1.0 - ak * uv);
-  const double aer_ref1 = x * aa1 * (1.0 - Ev * emak);   // exp_fast(-taup/aa1) = exp_fast(-taup/uv - ak taup)
+  const double aer_ref1 = x * aa1 * (1.0 - Ev * emak);   // exp_clamp(-taup/aa1) = exp_clamp(-taup/uv - ak taup)
   const double aer_ref2 = y * aa2 * (1.0 - Ev * eak);
   const double aer_ref3 = z * S.aa3 * (1.0 - Ev * Eu);
   const double aer_ref = (aer_ref1 + aer_ref2 + aer_ref3) * inv_usuv;
@@ -614,8 +630,8 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double Res_6s = (c[SM_REST1] + c[SM_REST2] * tt + c[SM_REST3] * (tt * tt)) + c[SM_REST4] * (tt * tt * tt);
   const double atm_ref = ray_ref - Res_ray + aer_ref - Res_aer + Res_6s;
 
-  const double ta_ss = exp_fast(-tautot * inv_us);
-  const double ta_oo = exp_fast(-tautot * inv_uv);
+  const double ta_ss = exp_clamp(-tautot * inv_us);
+  const double ta_oo = exp_clamp(-tautot * inv_uv);
   const double ta_sd = ttetas - ta_ss;
   const double ta_do = ttetav - ta_oo;
 

@@ -130,66 +130,192 @@ __constant__ double c_theta2[12];   // 2 * (pi/180) * theta for theta = 10..80 s
 constexpr int kLidfSpw = SPART_LIDF_SPW;
 
 // Leaf inclination distribution for the kLidfSpw samples of a warp (sailh.py:351-398).
-// The (sample, angle) fixed-point iterations need between 1 and ~120 steps each, so they are
-// treated as a queue of 12 * kLidfSpw tasks.  The hot loop is only "step if running"; a lane
-// that converges just clears `running` and keeps its result in registers.  As soon as
-// SPART_LIDF_BATCH lanes are idle they write their results and receive new tasks in one
-// hand-out (doing either per converged lane would execute divergent code on almost every
-// step).  sA/sB: the warp's LIDFa/LIDFb values.  Results F(theta) go straight to global
-// memory at out[ang * stride_ang + smp * stride_smp] (8-byte scattered writes, 96 B per
-// sample in total), so the kernel needs almost no shared memory; nvalid = number of real
-// samples of this warp.
-__device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, double* __restrict__ out,
-                                          int64_t stride_ang, int64_t stride_smp, int nvalid) {
+//
+// The reference's dcum is the fixed-point iteration x <- x + (y(x) - x + theta2)/2,
+// y = a sin x + b/2 sin 2x, stopped at |dx| <= 1e-8; its result depends on the number of steps
+// taken (1 ... ~120), so the sequence of iterates has to be reproduced, not just its limit.
+// The iterates are reproduced in two stages:
+//   A  exact steps (one sincos each) until the remaining distance to the fixed point is below
+//      ~SPART_LIDF_TAU: |dx| <= TAU (1 - y'(x))/2;
+//   B  from that iterate x_s on, y is replaced by its degree-7 Taylor polynomial around x_s.
+//      |x - x_s| <= ~TAU = 1.6e-2 for all later iterates, so the truncation error is below
+//      65/8! * TAU^8 = 7e-18 and the map u <- g(u) = (u + y~(u) + theta2 - x_s)/2 is one
+//      Horner evaluation (7 FMA) per step instead of a sincos.  Stage B continues the SAME
+//      sequence with the same stopping rule; against the step-by-step iteration the final
+//      F values agree to 1e-15 over the whole |a| + |b| <= 1 domain (tools/check_lidf_taylor.py).
+// Both stages run as a warp-wide task queue over the 12 * kLidfSpw (sample, angle) pairs: a
+// lane that finishes a task goes idle and as soon as SPART_LIDF_BATCH lanes are idle they are
+// all handed new tasks (handing out per finished lane would execute the divergent hand-out
+// code on almost every step).  sA/sB: the warp's LIDFa/LIDFb; sX: per-task hand-over value
+// (x_s, or 2 y + theta2 for a task that already converged in stage A, flagged in sDone).
+// Results F(theta) go to global memory at out[ang * stride_ang + smp * stride_smp].
+#define SPART_LIDF_TAU 1.6e-2
+#ifndef SPART_LIDF_ASTEPS
+#define SPART_LIDF_ASTEPS 2      // exact steps per bookkeeping round
+#endif
+#ifndef SPART_LIDF_BSTEPS
+#define SPART_LIDF_BSTEPS 16     // polynomial steps per bookkeeping round
+#endif
+#ifndef SPART_LIDF_BATCH_B
+#define SPART_LIDF_BATCH_B 8     // idle lanes that trigger a stage-B hand-out (its set-up costs a sincos)
+#endif
+constexpr int kLidfTasks = 12 * kLidfSpw;
+
+__device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, double* sX, unsigned char* sDone,
+                                          double* __restrict__ out, int64_t stride_ang, int64_t stride_smp,
+                                          int nvalid) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int ntask = 12 * kLidfSpw;
-  int next = 32;                 // warp-uniform: first unassigned task; task t -> angle t / SPW, sample t % SPW
-  int ang = 0, smp = lane;
-  double a = sA[lane], b = sB[lane];
-  double theta2 = c_theta2[0];
-  double x = theta2, y = 0.0;
-  bool running = true;
-  if (a > 1.0) {                 // sailh.py:371-372: closed form F = 1 - cos(theta), no iteration
-    y = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2)) - theta2);
-    running = false;
-  }
-  int iters = 0;                 // warp-uniform runaway guard (non-convergent garbage input)
-  while (true) {
-    if (running) running = !dcum_step(a, b, theta2, x, y);
-    const unsigned idle = __ballot_sync(full, !running);
-    const int nidle = __popc(idle);
-    if (next < ntask) {
-      if (nidle >= SPART_LIDF_BATCH) {
-        if (!running) {
-          if (smp < nvalid) out[ang * stride_ang + smp * stride_smp] = (2.0 * y + theta2) * (1.0 / SPART_PI);
-          const int task = next + __popc(idle & lt_mask);
-          if (task < ntask) {
-            ang = task / kLidfSpw;
-            smp = task % kLidfSpw;
-            a = sA[smp];
-            b = sB[smp];
-            theta2 = c_theta2[ang];
-            x = theta2;
-            running = true;
-            if (a > 1.0) {
-              y = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2)) - theta2);
-              running = false;
-            }
-          } else {
-            smp = kLidfSpw;      // nothing left to write for this lane
-          }
-        }
-        next += nidle;
-      }
-    } else if (nidle == 32) {
-      break;
+
+  // ---- stage A: exact steps ------------------------------------------------------------
+  {
+    int next = 32;                 // warp-uniform: first unassigned task; task t -> angle t / SPW, sample t % SPW
+    int task = lane;
+    double a = sA[lane], b = sB[lane];
+    double theta2 = c_theta2[0];
+    double x = theta2, y = 0.0;
+    bool running = true, conv = false;
+    if (a > 1.0) {                 // sailh.py:371-372: closed form F = 1 - cos(theta), no iteration
+      y = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2)) - theta2);
+      running = false;
+      conv = true;
     }
-    if (++iters > (1 << 22)) break;
+    int iters = 0;                 // warp-uniform runaway guard (non-convergent garbage input)
+    while (true) {
+#pragma unroll
+      for (int rep = 0; rep < SPART_LIDF_ASTEPS; ++rep) {
+        if (running) {
+          double s, c;
+          sincos_small(x, s, c);
+          y = s * fma(b, c, a);                                  // a sin x + b/2 sin 2x
+          const double dx = fma(0.5, y, 0.5 * (theta2 - x));     // (y - x + theta2) / 2
+          x += dx;
+          const double adx = fabs(dx);
+          const double yp = fma(a, c, b * fma(2.0 * c, c, -1.0));   // y'(x) = a cos x + b cos 2x
+          conv = !(adx > 1e-8);                                  // the reference's stop (NaN stops too)
+          running = !(conv || adx <= (0.5 * SPART_LIDF_TAU) * (1.0 - yp));
+        }
+      }
+      const unsigned idle = __ballot_sync(full, !running);
+      const int nidle = __popc(idle);
+      if (next < kLidfTasks) {
+        if (nidle >= SPART_LIDF_BATCH) {
+          if (!running) {
+            sX[task] = conv ? 2.0 * y + theta2 : x;
+            sDone[task] = conv ? 1 : 0;
+            task = next + __popc(idle & lt_mask);
+            if (task < kLidfTasks) {
+              const int ang = task / kLidfSpw, smp = task % kLidfSpw;
+              a = sA[smp];
+              b = sB[smp];
+              theta2 = c_theta2[ang];
+              x = theta2;
+              running = true;
+              conv = false;
+              if (a > 1.0) {
+                y = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2)) - theta2);
+                running = false;
+                conv = true;
+              }
+            } else {
+              task = -1;           // nothing left for this lane
+            }
+          }
+          next += nidle;
+        }
+      } else if (nidle == 32) {
+        break;
+      }
+      if (++iters > (1 << 22)) break;
+    }
+    if (task >= 0) {               // every lane ends idle with its last task's hand-over value in registers
+      sX[task] = conv ? 2.0 * y + theta2 : x;
+      sDone[task] = conv ? 1 : 0;
+    }
   }
-  // every lane ends idle with its last result still in registers
-  if (smp < nvalid) out[ang * stride_ang + smp * stride_smp] = (2.0 * y + theta2) * (1.0 / SPART_PI);
+  __syncwarp();
+
+  // ---- stage B: Taylor-model steps -------------------------------------------------------
+  {
+    int next = 0;
+    int ang = 0, smp = kLidfSpw;   // no task yet
+    double g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0;
+    double u = 0.0, uf = 0.0, unf = 0.0, k0 = 0.0, theta2 = 0.0;
+    double num = 0.0;              // 2 y + theta2 of a task that converged in stage A
+    bool direct = false;
+    bool running = false;
+    int iters = 0;
+    while (true) {
+      // SPART_LIDF_BSTEPS polynomial steps per bookkeeping round, branch-free: a lane that
+      // converges inside the round freezes (u, u_new) of its last step with selects
+#pragma unroll
+      for (int rep = 0; rep < SPART_LIDF_BSTEPS; ++rep) {
+        double un = fma(g7, u, g6);
+        un = fma(un, u, g5);
+        un = fma(un, u, g4);
+        un = fma(un, u, g3);
+        un = fma(un, u, g2);
+        un = fma(un, u, g1);
+        un = fma(un, u, g0);
+        const bool stop = !(fabs(un - u) > 1e-8);
+        const bool fin = running && stop;
+        uf = fin ? u : uf;
+        unf = fin ? un : unf;
+        u = running ? un : u;
+        running = running && !stop;
+      }
+      const unsigned idle = __ballot_sync(full, !running);
+      const int nidle = __popc(idle);
+      if (next < kLidfTasks) {
+        if (nidle >= SPART_LIDF_BATCH_B || next == 0) {
+          if (!running) {
+            // y~(u) = 2 u_new - u - k0, so 2 y + theta2 = 4 u_new - 2 u - 2 k0 + theta2
+            if (smp < nvalid)
+              out[ang * stride_ang + smp * stride_smp] =
+                  (direct ? num : 2.0 * (2.0 * unf - uf - k0) + theta2) * (1.0 / SPART_PI);
+            const int task = next + __popc(idle & lt_mask);
+            if (task < kLidfTasks) {
+              ang = task / kLidfSpw;
+              smp = task % kLidfSpw;
+              theta2 = c_theta2[ang];
+              const double xs = sX[task];
+              direct = sDone[task] != 0;
+              if (direct) {
+                num = xs;          // converged in stage A: xs already is 2 y + theta2
+              } else {
+                const double a = sA[smp], b = sB[smp];
+                double s, c;
+                sincos_small(xs, s, c);
+                const double s2 = 2.0 * s * c, c2 = fma(2.0 * c, c, -1.0);
+                k0 = theta2 - xs;
+                // g(u) = (u + y~(u) + k0) / 2 with y~ = sum_k y^(k)(xs) u^k / k!
+                g0 = 0.5 * (fma(a, s, 0.5 * b * s2) + k0);
+                g1 = 0.5 * (1.0 + fma(a, c, b * c2));
+                g2 = -(0.5 / 2.0) * fma(a, s, 2.0 * b * s2);
+                g3 = -(0.5 / 6.0) * fma(a, c, 4.0 * b * c2);
+                g4 = (0.5 / 24.0) * fma(a, s, 8.0 * b * s2);
+                g5 = (0.5 / 120.0) * fma(a, c, 16.0 * b * c2);
+                g6 = -(0.5 / 720.0) * fma(a, s, 32.0 * b * s2);
+                g7 = -(0.5 / 5040.0) * fma(a, c, 64.0 * b * c2);
+                u = 0.0;
+                running = true;
+              }
+            } else {
+              smp = kLidfSpw;      // nothing left to write for this lane
+            }
+          }
+          next += nidle;
+        }
+      } else if (nidle == 32) {
+        break;
+      }
+      if (++iters > (1 << 22)) break;
+    }
+    if (smp < nvalid)
+      out[ang * stride_ang + smp * stride_smp] =
+          (direct ? num : 2.0 * (2.0 * unf - uf - k0) + theta2) * (1.0 / SPART_PI);
+  }
 }
 
 // workspace rows: the per-sample record followed by the 12 cumulative leaf-angle values
@@ -210,6 +336,8 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
             int64_t stride_ang, int64_t stride_smp) {
   constexpr int kWarps = kSampleThreads / 32;
   __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
+  __shared__ double sX[kWarps][kLidfTasks];
+  __shared__ unsigned char sDone[kWarps][kLidfTasks];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t base = ((int64_t)blockIdx.x * kWarps + warp) * kLidfSpw;   // first sample of this warp
   if (base >= n) return;
@@ -220,7 +348,7 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
   }
   __syncwarp();
   const int nvalid = (int)((n - base < kLidfSpw) ? (n - base) : kLidfSpw);
-  warp_lidf(sA[warp], sB[warp], out + base * stride_smp, stride_ang, stride_smp, nvalid);
+  warp_lidf(sA[warp], sB[warp], sX[warp], sDone[warp], out + base * stride_smp, stride_ang, stride_smp, nvalid);
 }
 
 // In-place F -> lidf = diff([0, F_1..F_12, 1]) on a [n][13] buffer whose first 12 entries per
