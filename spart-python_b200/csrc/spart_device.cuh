@@ -122,6 +122,28 @@ __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
   cs = __hiloint2double(__double2hiint(ca) ^ (((q + 1) & 2) << 30), __double2loint(ca));
 }
 
+// ---- reciprocal without the slow path ---------------------------------------------------------
+// `1.0 / x` compiles to MUFU.RCP64H + 5 DFMA + a range check that branches to an out-of-line
+// fix-up for subnormal / huge operands (~12 instructions and two basic-block boundaries per
+// division).  Every denominator on the band path is a normal number of moderate magnitude, so
+// the seed + two Newton steps suffice: 5 instructions, <= 1 ulp.  0 -> inf/NaN and NaN -> NaN as
+// with a true division; subnormal or > 2^1022 denominators are not supported.
+#ifndef SPART_FAST_RCP
+#define SPART_FAST_RCP 1
+#endif
+__device__ __forceinline__ double rcp_fast(double x) {
+#if !SPART_FAST_RCP
+  return 1.0 / x;
+#else
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+#endif
+}
+
 // ---- exp / log with constant-bank coefficients ----------------------------------------------
 // libdevice's exp/log rebuild each of their ~13 polynomial coefficients with two move
 // instructions per call (46 / ~100 SASS instructions per call, 15 / ~25 of them FP64).  These
@@ -136,6 +158,9 @@ __constant__ double c_explog_red[4] = {SPART_LOG2E, 6755399441055744.0, SPART_LN
 #ifndef SPART_FAST_EXP
 #define SPART_FAST_EXP 1
 #endif
+#ifndef SPART_ESTRIN
+#define SPART_ESTRIN 0
+#endif
 #ifndef SPART_FAST_LOG
 #define SPART_FAST_LOG 1
 #endif
@@ -148,10 +173,22 @@ __device__ __forceinline__ double exp_core(double x, int& k) {
   const double kd = t - magic;
   double r = fma(-kd, c_explog_red[2], x);
   r = fma(-kd, c_explog_red[3], r);
+#if SPART_ESTRIN
+  // Estrin's scheme: 15 FP64 operations instead of 11, but a dependency depth of 5 instead of 11
+  const double* c = c_exp_poly;
+  const double r2 = r * r;
+  const double a0 = fma(c[1], r, c[0]), a1 = fma(c[3], r, c[2]), a2 = fma(c[5], r, c[4]);
+  const double a3 = fma(c[7], r, c[6]), a4 = fma(c[9], r, c[8]), a5 = fma(c[11], r, c[10]);
+  const double r4 = r2 * r2;
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double r8 = r4 * r4;
+  return fma(b2, r8, fma(b1, r4, b0));
+#else
   double p = c_exp_poly[11];
 #pragma unroll
   for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
   return p;
+#endif
 }
 
 // Full-range exp, branch free: the argument is clamped to [-745.2, 709.8] with NaN-preserving
@@ -210,7 +247,7 @@ __device__ __forceinline__ double log_fast(double x) {
     e += 1;
   }
   const double m = __hiloint2double(mh, __double2loint(x));
-  const double s = (m - 1.0) / (m + 1.0);
+  const double s = (m - 1.0) * rcp_fast(m + 1.0);
   const double z = s * s;
   double p = c_log_poly[8];
 #pragma unroll
@@ -255,7 +292,7 @@ __device__ __forceinline__ double plate_tau(double K, const TauTable* tab) {
   // caller guarantees K > 0
   const double emk = exp_fast(-K);
   int idx;
-  double u, t = 1.0 / K;
+  double u, t = rcp_fast(K);
   if (K < 1.0) {
     idx = 0;
     u = 2.0 * K - 1.0;
@@ -265,9 +302,21 @@ __device__ __forceinline__ double plate_tau(double K, const TauTable* tab) {
     u = (t - tab->mid[idx]) * tab->invhalf[idx];
   }
   const double* c = tab->coef[idx];
+#if SPART_ESTRIN
+  static_assert(SPART_TAU_DEG == 16, "Estrin evaluation below is written for degree 16");
+  const double u2 = u * u;
+  const double a0 = fma(c[1], u, c[0]), a1 = fma(c[3], u, c[2]), a2 = fma(c[5], u, c[4]), a3 = fma(c[7], u, c[6]);
+  const double a4 = fma(c[9], u, c[8]), a5 = fma(c[11], u, c[10]), a6 = fma(c[13], u, c[12]), a7 = fma(c[15], u, c[14]);
+  const double u4 = u2 * u2;
+  const double b0 = fma(a1, u2, a0), b1 = fma(a3, u2, a2), b2 = fma(a5, u2, a4), b3 = fma(a7, u2, a6);
+  const double u8 = u4 * u4;
+  const double d0 = fma(b1, u4, b0), d1 = fma(b3, u4, b2);
+  const double p = fma(c[16], u8 * u8, fma(d1, u8, d0));
+#else
   double p = c[SPART_TAU_DEG];
 #pragma unroll
   for (int i = SPART_TAU_DEG - 1; i >= 0; --i) p = fma(p, u, c[i]);
+#endif
   if (K < 1.0) {
     const double e1 = fma(K, p, -0.57721566490153286061 - log_fast(K));
     return (1.0 - K) * emk + K * K * e1;
@@ -295,7 +344,7 @@ __device__ __forceinline__ LeafPar load_leaf(const double* __restrict__ P, int64
   L.CBC = P[P_CBC * ld + s];
   // PROSPECT-PRO switch, prospect_5d.py:148-155
   if ((L.PROT > 0.0 || L.CBC > 0.0) && L.Cdm > 0.0) L.Cdm = 0.0;
-  L.invN = 1.0 / L.N;
+  L.invN = rcp_fast(L.N);
   return L;
 }
 
@@ -317,7 +366,7 @@ __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* l
 
   // one plate, prospect_5d.py:208-214
   const double tt21 = tau * t21;
-  const double inv_d1 = 1.0 / (1.0 - r21 * r21 * tau * tau);
+  const double inv_d1 = rcp_fast(1.0 - r21 * r21 * tau * tau);
   const double Ta = t_alph * tt21 * inv_d1;
   const double Ra = r_alph + r21 * tau * Ta;
   const double t = t12 * tt21 * inv_d1;
@@ -327,23 +376,23 @@ __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* l
   double Rsub, Tsub;
   const double Nm1 = L.N - 1.0;
   if (r + t >= 1.0) {  // zero absorption, prospect_5d.py:233-235
-    Tsub = t / (t + (1.0 - t) * Nm1);
+    Tsub = t * rcp_fast(t + (1.0 - t) * Nm1);
     Rsub = 1.0 - Tsub;
   } else {
     const double D = sqrt((1.0 + r + t) * (1.0 + r - t) * (1.0 - r + t) * (1.0 - r - t));
     const double rq = r * r, tq = t * t;
-    const double a = (1.0 + rq - tq + D) / (2.0 * r);
-    const double b = (1.0 - rq + tq + D) / (2.0 * t);
+    const double a = (1.0 + rq - tq + D) * rcp_fast(2.0 * r);
+    const double b = (1.0 - rq + tq + D) * rcp_fast(2.0 * t);
     // b ** (N - 1): b >= 1 and |(N-1) ln b| is O(1), so exp_fast(y ln b) is accurate to a few ulp;
     // the exact cases of pow are kept (y == 0 -> 1, b == inf -> inf).
     const double bNm1 = (Nm1 == 0.0) ? 1.0 : exp_fast(Nm1 * log_fast(b));
     const double bN2 = bNm1 * bNm1;
     const double a2 = a * a;
-    const double inv_d2 = 1.0 / (a2 * bN2 - 1.0);
+    const double inv_d2 = rcp_fast(a2 * bN2 - 1.0);
     Rsub = a * (bN2 - 1.0) * inv_d2;
     Tsub = bNm1 * (a2 - 1.0) * inv_d2;
   }
-  const double inv_d3 = 1.0 / (1.0 - Rsub * r);  // prospect_5d.py:239-241
+  const double inv_d3 = rcp_fast(1.0 - Rsub * r);  // prospect_5d.py:239-241
   tran = Ta * Tsub * inv_d3;
   refl = Ra + Ta * Rsub * t * inv_d3;
 }
@@ -369,7 +418,7 @@ __device__ __forceinline__ void bsm_point(const SoilPar& S, const double* lc, do
       tw *= tw1;                 // exp_clamp(-2 kw film k)
       fk = fk * S.mu * (1.0 / (double)k);
       const double x = tw * rbac;
-      acc += (Rw + g * x / (1.0 - p * x)) * fk;
+      acc += (Rw + g * x * rcp_fast(1.0 - p * x)) * fk;
     }
     rwet = acc;
   }
@@ -385,7 +434,7 @@ __device__ __forceinline__ double sail_J1(double m, double k, double LAI, double
   if (fabs((m - k) * LAI) < 1e-6) {
     return 0.5 * (em + ek) * LAI * (1.0 - (1.0 / 12.0) * (k - m) * (k - m) * LAI * LAI);
   }
-  return (em - ek) / (k - m);
+  return (em - ek) * rcp_fast(k - m);
 }
 
 __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, double tau, double rs, double& rso,
@@ -404,19 +453,19 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
   const double w = G.sob * rho + G.sof * tau;
   const double a = 1.0 - sigf;
   const double m = sqrt(a * a - sigb * sigb);
-  const double rinf = (a - m) / sigb;
+  const double rinf = (a - m) * rcp_fast(sigb);
   const double rinf2 = rinf * rinf;
 
   const double e1 = exp_clamp(-m * LAI);
   const double e2 = e1 * e1;
   const double tau_ss = G.tau_ss, tau_oo = G.tau_oo;
-  const double inv_km = 1.0 / (k + m), inv_Km = 1.0 / (K + m);
+  const double inv_km = rcp_fast(k + m), inv_Km = rcp_fast(K + m);
   const double J1k = sail_J1(m, k, LAI, e1, tau_ss);
   const double J2k = (1.0 - tau_ss * e1) * inv_km;   // calcJ2 at x = 0 (sailh.py:172-177)
   const double J1K = sail_J1(m, K, LAI, e1, tau_oo);
   const double J2K = (1.0 - tau_oo * e1) * inv_Km;
   const double re = rinf * e1;
-  const double inv_den = 1.0 / (1.0 - rinf2 * rinf2);
+  const double inv_den = rcp_fast(1.0 - rinf2 * rinf2);
 
   const double s1 = sf + rinf * sb, s2 = sf * rinf + sb;
   const double v1 = vf + rinf * vb, v2 = vf * rinf + vb;
@@ -433,10 +482,10 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
 
   const double T1 = v2 * s1 * (Z - J1k * tau_oo) * inv_Km + v1 * s2 * (Z - J1K * tau_ss) * inv_km;
   const double T2 = -(Qoo * rho_sd + Poo * tau_sd) * rinf;
-  const double rho_sod = (T1 + T2) / (1.0 - rinf2);
+  const double rho_sod = (T1 + T2) * rcp_fast(1.0 - rinf2);
   const double rho_so = rho_sod + w * G.sumpso;
 
-  const double rs_den = rs / (1.0 - rs * rho_dd);
+  const double rs_den = rs * rcp_fast(1.0 - rs * rho_dd);
   rso = rho_so + rs * G.pso2w + ((tau_sd + tau_ss * rs * rho_dd) * tau_oo + (tau_sd + tau_ss) * tau_do) * rs_den;
   rdo = rho_do + (tau_oo + tau_do) * tau_dd * rs_den;
   rsd = rho_sd + (tau_ss + tau_sd) * tau_dd * rs_den;
@@ -464,6 +513,8 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   const double Cs = cos_ttli * cos_tts, Ss = sin_ttli * sin_tts;
   const double Co = cos_ttli * cos_tto, So = sin_ttli * sin_tto;
   const double As = fmax(Ss, Cs), Ao = fmax(So, Co);
+  // true divisions: the quotient is exactly -1 whenever Cs >= Ss (As == Cs), and acos amplifies a
+  // 1-ulp deviation from -1 to 1e-8
   const double bts = acos(-Cs / As), bto = acos(-Co / Ao);
   chi_o = 2.0 / SPART_PI * ((bto - SPART_PI / 2.0) * Co + sin(bto) * So);
   chi_s = 2.0 / SPART_PI * ((bts - SPART_PI / 2.0) * Cs + sin(bts) * Ss);
@@ -477,8 +528,8 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   const double T2 = sin(bt2) * (2.0 * As * Ao + Ss * So * cos(bt1) * cos(bt3));
   const double Jmin = bt2 * T1 - T2;
   const double Jplus = (SPART_PI - bt2) * T1 + T2;
-  frho = fmax(0.0, Jplus / (2.0 * SPART_PI * SPART_PI));
-  ftau = fmax(0.0, -Jmin / (2.0 * SPART_PI * SPART_PI));
+  frho = fmax(0.0, Jplus * (1.0 / (2.0 * SPART_PI * SPART_PI)));
+  ftau = fmax(0.0, -Jmin * (1.0 / (2.0 * SPART_PI * SPART_PI)));
 }
 
 // ---- hot-spot integrals (sailh.py:116-135, 216-219) --------------------------------------
@@ -500,14 +551,14 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
   const double Amin = A0 - S;
   double A = A0, Cq = 0.0, alpha = 0.0;
   if (dso != 0.0) {
-    alpha = (dso / q) * 2.0 / (k + K);
-    Cq = S / alpha;
+    alpha = (dso * rcp_fast(q)) * 2.0 * rcp_fast(k + K);
+    Cq = S * rcp_fast(alpha);
   } else {
     A = Amin;   // sailh.py:127
   }
   double L = 1.0;
-  if (alpha > 0.0) L = fmin(L, 40.0 / alpha);
-  if (Amin > 0.0) L = fmin(L, 40.0 / Amin);
+  if (alpha > 0.0) L = fmin(L, 40.0 * rcp_fast(alpha));
+  if (Amin > 0.0) L = fmin(L, 40.0 * rcp_fast(Amin));
   const double h = L * (1.0 / SPART_NP);
   const double ah = alpha * h;
   double gnode[SPART_NQ];
@@ -529,7 +580,7 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
   }
   total *= 0.5 * h;
   if (L < 1.0 && alpha * L >= 40.0 * (1.0 - 1e-12)) {  // analytic pure-exponential remainder
-    total += exp_fast(Cq - A * L) * (1.0 - exp_fast(-A * (1.0 - L))) / A;
+    total += exp_fast(Cq - A * L) * (1.0 - exp_fast(-A * (1.0 - L))) * rcp_fast(A);
   }
   sumpso_ilai = total * LAI;
 
@@ -593,14 +644,14 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double opb = c[SM_OPB], omb = c[SM_OMB], g3 = c[SM_G3], h3 = c[SM_H3], akd3 = c[SM_AKD3];
 
   const double us2 = us * us;
-  const double inv_q = 1.0 / (1.0 - ak2 * us2);
+  const double inv_q = rcp_fast(1.0 - ak2 * us2);
   const double e = -0.75 * us2 * wo * inv_q;
   const double f = -0.25 * h3 * us2 * wo * inv_q;
   const double dp = e * inv_us * (1.0 / 3.0) + us * f;
   const double d = e + f;
   const double eak = exp_clamp(ak * taup);
-  const double emak = 1.0 / eak;
-  const double inv_delta = 1.0 / (eak * c[SM_OPB2] - emak * c[SM_OMB2]);
+  const double emak = rcp_fast(eak);
+  const double inv_delta = rcp_fast(eak * c[SM_OPB2] - emak * c[SM_OMB2]);
   const double ss = us * inv_q;
   const double q1 = 2.0 + 3.0 * us + h3 * us * (1.0 + 2.0 * us);
   const double q2 = 2.0 - 3.0 * us - h3 * us * (1.0 - 2.0 * us);
@@ -615,8 +666,8 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   const double z = d - g3uv * dp + wo * aer_phase * 0.25;
   const double x = c1 - g3uv * cp1;
   const double y = c2 - g3uv * cp2;
-  const double aa1 = uv / (1.0 + ak * uv);
-  const double aa2 = uv / (1.0 - ak * uv);
+  const double aa1 = uv * rcp_fast(1.0 + ak * uv);
+  const double aa2 = uv * rcp_fast(1.0 - ak * uv);
   const double aer_ref1 = x * aa1 * (1.0 - Ev * emak);   // exp_clamp(-taup/aa1) = exp_clamp(-taup/uv - ak taup)
   const double aer_ref2 = y * aa2 * (1.0 - Ev * eak);
   const double aer_ref3 = z * S.aa3 * (1.0 - Ev * Eu);
@@ -637,11 +688,11 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
 
   // SPART.py:243-252
   const double ra_dd = s, ra_so = atm_ref;
-  const double inv_ms = 1.0 / (1.0 - rv_dd * ra_dd);
+  const double inv_ms = rcp_fast(1.0 - rv_dd * ra_dd);
   const double rtoa0 = ra_so + ta_ss * rv_so * ta_oo;
   const double rtoa1 = (ta_sd * rv_do + ta_ss * rv_sd * ra_dd * rv_do) * ta_oo * inv_ms;
   const double rtoa2 = (ta_ss * rv_sd + ta_sd * rv_dd) * ta_do * inv_ms;
-  R_TOC = (ta_ss * rv_so + ta_sd * rv_do) / (ta_ss + ta_sd);
+  R_TOC = (ta_ss * rv_so + ta_sd * rv_do) * rcp_fast(ta_ss + ta_sd);
   R_TOA = tg * (rtoa0 + rtoa1 + rtoa2);
   L_TOA = (conv_ea * etscale) * R_TOA;
 }

@@ -392,8 +392,8 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   const double tan_tts = tan(tts * SPART_DEG2RAD), tan_tto = tan(tto * SPART_DEG2RAD);
   const double cos_psi = cos(psi_rad);
   const double dso = sqrt(tan_tts * tan_tts + tan_tto * tan_tto - 2.0 * tan_tts * tan_tto * cos_psi);
-  const double inv_cc = SPART_PI / (cos_tts * cos_tto);
-  const double inv_cs = 1.0 / cos_tts, inv_co = 1.0 / cos_tto;
+  const double inv_cs = rcp_fast(cos_tts), inv_co = rcp_fast(cos_tto);
+  const double inv_cc = SPART_PI * inv_cs * inv_co;
 
   if (uniform_geometry) {
     if (tid < 13) {
@@ -447,7 +447,7 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   rec[R_TAUOO * n + s] = tau_oo;
   rec[R_SUMPSO * n + s] = sumpso;
   rec[R_PSO2W * n + s] = pso2w;
-  rec[R_Z * n + s] = (1.0 - tau_ss * tau_oo) / (K + k);
+  rec[R_Z * n + s] = (1.0 - tau_ss * tau_oo) * rcp_fast(K + k);
 
   // BSM soil-vector weights and Poisson mean (bsm.py:49-51, 101)
   {
@@ -460,7 +460,7 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     rec[R_F1 * n + s] = soil_spectrum ? 1.0 : B * slat;
     rec[R_F2 * n + s] = soil_spectrum ? 0.0 : B * clat * slon;
     rec[R_F3 * n + s] = soil_spectrum ? 0.0 : B * clat * clon;
-    const double mu = (P[P_SMP * ld + s] - 5.0) / P[P_SMC * ld + s];
+    const double mu = (P[P_SMP * ld + s] - 5.0) * rcp_fast(P[P_SMC * ld + s]);
     rec[R_MU * n + s] = mu;
     rec[R_EMU * n + s] = exp_fast(-mu);
   }
@@ -468,7 +468,7 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   // SMAC per-sample scalars (smac.py:98-102, 129-141)
   {
     const double us = cos_tts, uv = cos_tto;    // cos(tts*cdr), cos(tto*cdr)
-    const double Peq = P[P_PA * ld + s] / 1013.25;
+    const double Peq = P[P_PA * ld + s] * (1.0 / 1013.25);
     const double m = inv_cs + inv_co;
     const double crd = 180.0 / SPART_PI;
     double cksi = -((us * uv) + (sqrt(1.0 - us * us) * sqrt(1.0 - uv * uv) * cos(rel * crd)));
@@ -487,16 +487,16 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     rec[R_RAYPH * n + s] = 0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742;
     rec[R_INVUS * n + s] = inv_cs;
     rec[R_INVUV * n + s] = inv_co;
-    rec[R_INV1PUS * n + s] = 1.0 / (1.0 + us);
-    rec[R_INV1PUV * n + s] = 1.0 / (1.0 + uv);
-    rec[R_AA3 * n + s] = us * uv / (us + uv);
+    rec[R_INV1PUS * n + s] = rcp_fast(1.0 + us);
+    rec[R_INV1PUV * n + s] = rcp_fast(1.0 + uv);
+    rec[R_AA3 * n + s] = us * uv * rcp_fast(us + uv);
     // extraterrestrial radiance scale (SPART.py:345-353)
-    const double b = 2.0 * SPART_PI * P[P_DOY * ld + s] / 365.0;
+    const double b = 2.0 * SPART_PI * P[P_DOY * ld + s] * (1.0 / 365.0);
     double sb, cb, s2b, c2b;
     sincos(b, &sb, &cb);
     sincos(2.0 * b, &s2b, &c2b);
     const double cf = 1.00011 + 0.034221 * cb + 0.00128 * sb + 0.000719 * c2b + 0.000077 * s2b;
-    rec[R_ETSCALE * n + s] = cf * us / SPART_PI;
+    rec[R_ETSCALE * n + s] = cf * us * (1.0 / SPART_PI);
   }
 }
 
