@@ -144,6 +144,24 @@ __device__ __forceinline__ double rcp_fast(double x) {
 #endif
 }
 
+// sqrt from the rsqrt seed and two coupled Newton steps (<= 1 ulp), branch free: sqrt(0) = 0,
+// negative / NaN -> NaN.  (+inf and subnormal arguments are not supported.)
+__device__ __forceinline__ double sqrt_fast(double x) {
+#if !SPART_FAST_RCP
+  return sqrt(x);
+#else
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = (x == 0.0) ? 0.0 : r;
+  double g = x * r, h = 0.5 * r;
+  double e = fma(-h, g, 0.5);
+  g = fma(g, e, g);
+  h = fma(h, e, h);
+  e = fma(-h, g, 0.5);
+  return fma(g, e, g);
+#endif
+}
+
 // ---- exp / log with constant-bank coefficients ----------------------------------------------
 // libdevice's exp/log rebuild each of their ~13 polynomial coefficients with two move
 // instructions per call (46 / ~100 SASS instructions per call, 15 / ~25 of them FP64).  These
@@ -379,7 +397,7 @@ __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* l
     Tsub = t * rcp_fast(t + (1.0 - t) * Nm1);
     Rsub = 1.0 - Tsub;
   } else {
-    const double D = sqrt((1.0 + r + t) * (1.0 + r - t) * (1.0 - r + t) * (1.0 - r - t));
+    const double D = sqrt_fast((1.0 + r + t) * (1.0 + r - t) * (1.0 - r + t) * (1.0 - r - t));
     const double rq = r * r, tq = t * t;
     const double a = (1.0 + rq - tq + D) * rcp_fast(2.0 * r);
     const double b = (1.0 - rq + tq + D) * rcp_fast(2.0 * t);
@@ -452,7 +470,7 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
   const double vf = dof * rho + dob * tau;
   const double w = G.sob * rho + G.sof * tau;
   const double a = 1.0 - sigf;
-  const double m = sqrt(a * a - sigb * sigb);
+  const double m = sqrt_fast(a * a - sigb * sigb);
   const double rinf = (a - m) * rcp_fast(sigb);
   const double rinf2 = rinf * rinf;
 
@@ -516,16 +534,22 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   // true divisions: the quotient is exactly -1 whenever Cs >= Ss (As == Cs), and acos amplifies a
   // 1-ulp deviation from -1 to 1e-8
   const double bts = acos(-Cs / As), bto = acos(-Co / Ao);
-  chi_o = 2.0 / SPART_PI * ((bto - SPART_PI / 2.0) * Co + sin(bto) * So);
-  chi_s = 2.0 / SPART_PI * ((bts - SPART_PI / 2.0) * Cs + sin(bts) * Ss);
+  double sbto, cbto, sbts, cbts, s2, c2, s1, c1, s3, c3;   // all arguments lie in [0, 2 pi]
+  sincos_small(bto, sbto, cbto);
+  sincos_small(bts, sbts, cbts);
+  chi_o = 2.0 / SPART_PI * ((bto - SPART_PI / 2.0) * Co + sbto * So);
+  chi_s = 2.0 / SPART_PI * ((bts - SPART_PI / 2.0) * Cs + sbts * Ss);
   const double delta1 = fabs(bts - bto);
   const double delta2 = SPART_PI - fabs(bts + bto - SPART_PI);
   const double Tot = psi_rad + delta1 + delta2;
   const double bt1 = fmin(psi_rad, delta1);
   const double bt3 = fmax(psi_rad, delta2);
   const double bt2 = Tot - bt1 - bt3;
+  sincos_small(bt2, s2, c2);
+  sincos_small(bt1, s1, c1);
+  sincos_small(bt3, s3, c3);
   const double T1 = 2.0 * Cs * Co + Ss * So * cos_psi;
-  const double T2 = sin(bt2) * (2.0 * As * Ao + Ss * So * cos(bt1) * cos(bt3));
+  const double T2 = s2 * (2.0 * As * Ao + Ss * So * c1 * c3);
   const double Jmin = bt2 * T1 - T2;
   const double Jplus = (SPART_PI - bt2) * T1 + T2;
   frho = fmax(0.0, Jplus * (1.0 / (2.0 * SPART_PI * SPART_PI)));
@@ -547,7 +571,7 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
 __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI, double q, double dso,
                                                   double& sumpso_ilai, double& pso2w) {
   const double A0 = (K + k) * LAI;
-  const double S = sqrt(K * k) * LAI;
+  const double S = sqrt_fast(K * k) * LAI;
   const double Amin = A0 - S;
   double A = A0, Cq = 0.0, alpha = 0.0;
   if (dso != 0.0) {
