@@ -386,14 +386,17 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   const double tts = P[P_SZA * ld + s], tto = P[P_VZA * ld + s], rel = P[P_RAA * ld + s];
   const double psi = fabs(rel - 360.0 * rint(rel / 360.0));
   const double psi_rad = psi * SPART_DEG2RAD;
-  double sin_tts, cos_tts, sin_tto, cos_tto;
-  sincos(tts * SPART_DEG2RAD, &sin_tts, &cos_tts);
-  sincos(tto * SPART_DEG2RAD, &sin_tto, &cos_tto);
-  const double tan_tts = tan(tts * SPART_DEG2RAD), tan_tto = tan(tto * SPART_DEG2RAD);
-  const double cos_psi = cos(psi_rad);
-  const double dso = sqrt(tan_tts * tan_tts + tan_tto * tan_tto - 2.0 * tan_tts * tan_tto * cos_psi);
+  // zenith angles and the folded azimuth are a few radians at most: bounded-range sincos
+  double sin_tts, cos_tts, sin_tto, cos_tto, sin_psi, cos_psi;
+  sincos_small(tts * SPART_DEG2RAD, sin_tts, cos_tts);
+  sincos_small(tto * SPART_DEG2RAD, sin_tto, cos_tto);
+  sincos_small(psi_rad, sin_psi, cos_psi);
+  (void)sin_psi;
   const double inv_cs = rcp_fast(cos_tts), inv_co = rcp_fast(cos_tto);
   const double inv_cc = SPART_PI * inv_cs * inv_co;
+  const double tan_tts = sin_tts * inv_cs, tan_tto = sin_tto * inv_co;
+  // like the reference, a rounding-negative radicand gives NaN (sailh.py:78)
+  const double dso = sqrt_fast(tan_tts * tan_tts + tan_tto * tan_tto - 2.0 * tan_tts * tan_tto * cos_psi);
 
   if (uniform_geometry) {
     if (tid < 13) {
@@ -453,8 +456,8 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   {
     const double B = P[P_B * ld + s];
     double slat, clat, slon, clon;
-    sincos(P[P_LAT * ld + s] * SPART_PI / 180.0, &slat, &clat);
-    sincos(P[P_LON * ld + s] * SPART_PI / 180.0, &slon, &clon);
+    sincos_small(P[P_LAT * ld + s] * SPART_PI / 180.0, slat, clat);
+    sincos_small(P[P_LON * ld + s] * SPART_PI / 180.0, slon, clon);
     // with a user-supplied dry-soil spectrum (bsm.py:42-43) the context's first soil vector IS that
     // spectrum and the weights are (1, 0, 0): rdry = 1 * spectrum + 0 + 0 exactly
     rec[R_F1 * n + s] = soil_spectrum ? 1.0 : B * slat;
@@ -493,8 +496,8 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     // extraterrestrial radiance scale (SPART.py:345-353)
     const double b = 2.0 * SPART_PI * P[P_DOY * ld + s] * (1.0 / 365.0);
     double sb, cb, s2b, c2b;
-    sincos(b, &sb, &cb);
-    sincos(2.0 * b, &s2b, &c2b);
+    sincos_small(b, sb, cb);
+    sincos_small(2.0 * b, s2b, c2b);
     const double cf = 1.00011 + 0.034221 * cb + 0.00128 * sb + 0.000719 * c2b + 0.000077 * s2b;
     rec[R_ETSCALE * n + s] = cf * us * (1.0 / SPART_PI);
   }
