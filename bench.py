@@ -48,10 +48,29 @@ BYTES_PER_SAMPLE = {"lidf_kernel": (2 + 12) * 8, "geometry_kernel": (12 + 12 + 3
                     "band_kernel": (32 + 12) * 8 + 13 * 3 * 8}
 
 
+def kernel_source_sha():
+    """Hash of the CUDA sources: the executed-flop counts in profiles/flop_per_sample.json are only
+    valid for the kernel build they were measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "spart-python_b200" / "csrc").glob("*")):
+        if f.suffix in (".cu", ".cuh", ".h"):
+            h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
 def load_flop_counts():
+    """Returns a note when the stored counts belong to another kernel build (roofline.achieved is
+    then still computed, but flagged)."""
     p = ROOT / "profiles" / "flop_per_sample.json"
-    if p.exists():
-        FLOP_PER_SAMPLE.update(json.loads(p.read_text()))
+    if not p.exists():
+        return "no profiles/flop_per_sample.json"
+    d = json.loads(p.read_text())
+    sha = d.pop("src_sha", None)
+    FLOP_PER_SAMPLE.update(d)
+    if sha != kernel_source_sha():
+        return f"flop counts measured on kernel sources {sha}, current sources {kernel_source_sha()}"
+    return None
 
 
 # ----------------------------------------------------------------------------- helpers
@@ -100,7 +119,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as e:  # NVML missing: report that instead of failing the bench
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -210,7 +229,7 @@ def run_ours(args):
     nb = st.n_bands
     params = synthetic_params_torch(n, 20261018 + CONFIG_ID + 7919 * rank, dev)
     out = torch.empty((n, nb, 3), dtype=torch.float64, device=dev)
-    load_flop_counts()
+    flop_note = load_flop_counts()
 
     # --- resident-input timing -------------------------------------------------------
     for _ in range(args.warmup):
@@ -304,7 +323,7 @@ def run_ours(args):
         "frac": (ach_tf / peaks["fp64_tflops"]) if ach_tf else None, "traffic": None,
         "peak_source": "DFMA-chain micro-benchmark measured live in this run (spart_measure_peaks)",
         "kernel_ms": kern_ms, "share_of_step": kern_ms[dominant] / (ms / args.steps),
-        "flop_per_simulation": FLOP_PER_SAMPLE,
+        "flop_per_simulation": FLOP_PER_SAMPLE, "flop_count_note": flop_note,
     }
     nbytes = BYTES_PER_SAMPLE[dominant] * n
     ach_gb = nbytes / (kern_ms[dominant] * 1e-3) / 1e9

@@ -33,6 +33,9 @@ def main(tag):
     summ = json.loads(buf.getvalue())
     (prof / f"{tag}_ncu_summary.json").write_text(json.dumps(summ, indent=1) + "\n")
     flop = {k: v["fp64_flop_per_unit"] for k, v in summ.items()}
+    sys.path.insert(0, str(ROOT))
+    import bench
+    flop["src_sha"] = bench.kernel_source_sha()     # the counts belong to this kernel build
     (prof / "flop_per_sample.json").write_text(json.dumps(flop, indent=1) + "\n")
     traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in summ.items()}
     (prof / "dram_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
