@@ -158,6 +158,13 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params
 int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
                            int32_t flags, void* workspace_dev, double* out_dev, void* stream);
 
+/* Replaces SMAC(angles, atm, coefs) (smac.py:14-213) for sensor `sensor`.  params_dev:
+ * [SPART_NPAR][ld]; only the angle and atmosphere rows 19..25 matter, the others must merely be
+ * finite.  out_dev: double [n][9][n_bands] in the field order of the reference's
+ * AtmosphericOptics: Ta_s, Ta_o, Tg, Ra_dd, Ra_so, Ta_ss, Ta_sd, Ta_oo, Ta_do. */
+int spart_smac(const SpartCtx* ctx, int32_t sensor, const double* params_dev, int64_t n, int64_t ld,
+               void* workspace_dev, double* out_dev, void* stream);
+
 /* Replaces SAILH(soil, leafopt, canopy, angles) on caller-supplied spectra (sailh.py:14-237).
  * params_dev: [SPART_NPAR][ld]; only the canopy and angle rows 15..21 matter, the others must
  * merely be finite.  soil_refl / leaf_refl / leaf_tran: double spectra of SPART_NWL_S (2162)

@@ -631,9 +631,11 @@ struct AtmSample {
   double inv_us, inv_uv, inv_1pus, inv_1puv, aa3;
 };
 
-__device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* c, double conv_ea, double etscale,
-                                              double rv_so, double rv_do, double rv_dd, double rv_sd,
-                                              double& R_TOC, double& R_TOA, double& L_TOA) {
+struct AtmOptics {   // AtmosphericOptics of the reference (smac.py:216-272)
+  double Ta_s, Ta_o, Tg, Ra_dd, Ra_so, Ta_ss, Ta_sd, Ta_oo, Ta_do;
+};
+
+__device__ __forceinline__ AtmOptics smac_band(const AtmSample& S, const double* c) {
   const double us = S.us, uv = S.uv, m = S.m, Peq = S.Peq, taup550 = S.taup550;
   const double inv_us = S.inv_us, inv_uv = S.inv_uv;
   const double taup = c[SM_A0TAUP] + c[SM_A1TAUP] * taup550;
@@ -707,11 +709,26 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
 
   const double ta_ss = exp_clamp(-tautot * inv_us);
   const double ta_oo = exp_clamp(-tautot * inv_uv);
-  const double ta_sd = ttetas - ta_ss;
-  const double ta_do = ttetav - ta_oo;
+  AtmOptics O;
+  O.Ta_s = ttetas;
+  O.Ta_o = ttetav;
+  O.Tg = tg;
+  O.Ra_dd = s;
+  O.Ra_so = atm_ref;
+  O.Ta_ss = ta_ss;
+  O.Ta_sd = ttetas - ta_ss;
+  O.Ta_oo = ta_oo;
+  O.Ta_do = ttetav - ta_oo;
+  return O;
+}
 
+__device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* c, double conv_ea, double etscale,
+                                              double rv_so, double rv_do, double rv_dd, double rv_sd,
+                                              double& R_TOC, double& R_TOA, double& L_TOA) {
+  const AtmOptics O = smac_band(S, c);
+  const double tg = O.Tg, ta_ss = O.Ta_ss, ta_sd = O.Ta_sd, ta_oo = O.Ta_oo, ta_do = O.Ta_do;
   // SPART.py:243-252
-  const double ra_dd = s, ra_so = atm_ref;
+  const double ra_dd = O.Ra_dd, ra_so = O.Ra_so;
   const double inv_ms = rcp_fast(1.0 - rv_dd * ra_dd);
   const double rtoa0 = ra_so + ta_ss * rv_so * ta_oo;
   const double rtoa1 = (ta_sd * rv_do + ta_ss * rv_sd * ra_dd * rv_do) * ta_oo * inv_ms;

@@ -674,6 +674,37 @@ band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   o[2] = L_TOA;
 }
 
+// SMAC alone (the reference's SMAC(angles, atm, coefs), smac.py:14-213): the nine
+// AtmosphericOptics arrays per (sample, band); thread = sample, blockIdx.x = band.
+__global__ void __launch_bounds__(kBandThreads)
+smac_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+            const double* __restrict__ band_table, int nb, double* __restrict__ out) {
+  __shared__ double s_c[SM_COUNT];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < SM_COUNT; i += blockDim.x) s_c[i] = band_table[(size_t)b * BT_COUNT + BT_SMAC + i];
+  __syncthreads();
+  const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
+  if (s >= n) return;
+  AtmSample A;
+  A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
+  A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s]; A.lpeq = rec[R_LPEQ * n + s];
+  A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
+  A.taup550 = P[P_AOT * ld + s];
+  A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
+  A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
+  const AtmOptics O = smac_band(A, s_c);
+  double* o = out + (size_t)s * 9 * nb + b;
+  o[0 * nb] = O.Ta_s;
+  o[1 * nb] = O.Ta_o;
+  o[2 * nb] = O.Tg;
+  o[3 * nb] = O.Ra_dd;
+  o[4 * nb] = O.Ra_so;
+  o[5 * nb] = O.Ta_ss;
+  o[6 * nb] = O.Ta_sd;
+  o[7 * nb] = O.Ta_oo;
+  o[8 * nb] = O.Ta_do;
+}
+
 // SAILH on caller-supplied spectra (the reference's SAILH(soil, leafopt, canopy, angles),
 // sailh.py:14-237): thread = wavelength (coalesced reads of the three input spectra and writes
 // of the four outputs), blockIdx.y = sample; the sample's canopy record is a broadcast load.
@@ -1298,6 +1329,26 @@ int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_
   if (rc) return rc;
   dim3 grid((SPART_NWL_S + kSpecChunk - 1) / kSpecChunk, (unsigned)((n + kSpecThreads - 1) / kSpecThreads));
   spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, out_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return SPART_OK;
+}
+
+int spart_smac(const SpartCtx* ctx, int32_t sensor, const double* params_dev, int64_t n, int64_t ld,
+               void* workspace_dev, double* out_dev, void* stream) {
+  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_smac");
+  if (rc) return rc;
+  if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "spart_smac: unknown sensor%s");
+  if (n == 0) return SPART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  double* rec = (double*)workspace_dev;
+  rc = launch_lidf(params_dev, n, ld, rec, st);
+  if (rc) return rc;
+  rc = launch_geometry(params_dev, n, ld, rec, 0, st);
+  if (rc) return rc;
+  const int nb = ctx->n_bands[sensor];
+  dim3 grid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
+  smac_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;

@@ -10,7 +10,7 @@ from .engine import Engine, default_engine
 from .model import SPART, SpectralBands, load_optical_parameters, load_sensor_info
 from .params import (Angles, AtmosphericProperties, CanopyStructure, LeafBiology, SoilParameters,
                      SoilParametersFromFile, pack_params)
-from .stages import (BSM, PROSPECT_5D, SAILH, bsm_batch, prospect_batch, sailh_batch,
+from .stages import (BSM, PROSPECT_5D, SAILH, SMAC, bsm_batch, prospect_batch, sailh_batch, smac_batch,
                      set_leaf_refl_trans_assumptions, set_soil_refl_trans_assumptions)
 from .tables import SENSOR_NAMES, synthetic_fullspectrum_sensorinfo
 
@@ -19,6 +19,6 @@ __all__ = [
     "AtmosphericProperties", "run_batch", "run_batch_params", "pack_batch", "pack_params",
     "row_as_dataframe", "Engine", "default_engine", "SpartError", "SENSOR_NAMES",
     "load_optical_parameters", "load_sensor_info", "synthetic_fullspectrum_sensorinfo",
-    "PROSPECT_5D", "BSM", "SAILH", "prospect_batch", "bsm_batch", "sailh_batch",
+    "PROSPECT_5D", "BSM", "SAILH", "SMAC", "prospect_batch", "bsm_batch", "sailh_batch", "smac_batch",
     "set_leaf_refl_trans_assumptions", "set_soil_refl_trans_assumptions",
 ]

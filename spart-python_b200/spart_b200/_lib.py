@@ -25,7 +25,7 @@ FP32 = 32
 EXPORTS = (
     "spart_abi_version", "spart_last_error", "spart_device_count", "spart_create", "spart_destroy",
     "spart_workspace_bytes", "spart_forward_bands", "spart_forward_bands_host", "spart_forward_spectrum",
-    "spart_sailh", "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
+    "spart_smac", "spart_sailh", "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
 )
 
 
@@ -77,6 +77,7 @@ def load():
                                              c_void_p]
     lib.spart_forward_spectrum.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                            c_void_p]
+    lib.spart_smac.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.spart_sailh.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                 c_void_p, c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]

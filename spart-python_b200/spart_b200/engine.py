@@ -164,6 +164,19 @@ class Engine:
                                                    out.data_ptr(), stream), "spart_forward_spectrum")
         return out
 
+    def smac(self, params, sensor, out=None):
+        """SMAC alone.  params: CUDA float64 [27, n] (angle and atmosphere rows used)
+        -> CUDA float64 [n, 9, nb]: Ta_s, Ta_o, Tg, Ra_dd, Ra_so, Ta_ss, Ta_sd, Ta_oo, Ta_do."""
+        handle, st = self.sensor(sensor)
+        params, n, ld = self._prep(params)
+        if out is None:
+            out = torch.empty((n, 9, st.n_bands), dtype=torch.float64, device=self.device)
+        ws = torch.empty(self.lib.spart_workspace_bytes(handle, n) // 8, dtype=torch.float64, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.spart_smac(handle, 0, params.data_ptr(), n, ld, ws.data_ptr(), out.data_ptr(), stream),
+                   "spart_smac")
+        return out
+
     def sailh(self, params, soil_refl, leaf_refl, leaf_tran, out=None):
         """SAILH on caller-supplied spectra.  params: CUDA float64 [27, n] (canopy and angle rows
         used); spectra: CUDA float64 [2162] (shared by all samples) or [n, 2162].

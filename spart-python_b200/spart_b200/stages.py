@@ -92,6 +92,35 @@ def sailh_batch(soil_refl, leaf_refl, leaf_tran, canopy, angles):
     return eng.sailh(P, *spec).cpu().numpy()
 
 
+ATM_FIELDS = ("Ta_s", "Ta_o", "Tg", "Ra_dd", "Ra_so", "Ta_ss", "Ta_sd", "Ta_oo", "Ta_do")
+
+
+class AtmosphericOptics:
+    """Atmospheric reflectance / transmittance arrays of SMAC, each [1, nb] (reference smac.py:216-272)."""
+
+    def __init__(self, Ta_s, Ta_o, Tg, Ra_dd, Ra_so, Ta_ss, Ta_sd, Ta_oo, Ta_do):
+        self.Ta_s, self.Ta_o, self.Tg, self.Ra_dd, self.Ra_so = Ta_s, Ta_o, Tg, Ra_dd, Ra_so
+        self.Ta_ss, self.Ta_sd, self.Ta_oo, self.Ta_do = Ta_ss, Ta_sd, Ta_oo, Ta_do
+
+
+def smac_batch(angles, atm, sensor):
+    """angles [n, 3], atm [n, 4] (aot550 uo3 uh2o Pa) -> [n, 9, nb] in the order of ATM_FIELDS.
+    `sensor` is a shipped sensor name or a sensorinfo dict (its 'SMAC_coef' are the coefficients)."""
+    angles = np.atleast_2d(np.asarray(angles, dtype=np.float64))
+    atm = np.atleast_2d(np.asarray(atm, dtype=np.float64))
+    eng = default_engine()
+    P = torch.from_numpy(_block(angles.shape[0], angles=((19, 22), angles), atm=((22, 26), atm))).to(eng.device)
+    return eng.smac(P, sensor).cpu().numpy()
+
+
+def SMAC(angles, atm, sensor):
+    """Reference-shaped SMAC(angles, atm, coefs) (smac.py:14-213).  The third argument is the sensor
+    name or the sensorinfo dict the coefficients belong to (the folded coefficient tables live on the
+    GPU per sensor, so a bare coefficient dict is not accepted)."""
+    out = smac_batch([angles.as_row()], [atm.as_row()], sensor)[0]
+    return AtmosphericOptics(*[out[i][None, :] for i in range(9)])
+
+
 def PROSPECT_5D(leafbio, optical_params=None):
     if (leafbio.PROT > 0.0 or leafbio.CBC > 0.0) and leafbio.Cdm > 0:
         print("WARNING: When setting PROT and/or CBC > 0. we\nassume that PROSPECT-PRO was called. Cdm will be\n"

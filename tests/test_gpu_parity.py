@@ -378,3 +378,18 @@ def test_multi_sensor_shares_the_per_sample_work(env):
         assert torch.equal(b, sb.run_batch_params(dev, "Sentinel2B-MSI", precision=prec, uniform_geometry=True))
     ha, hb = sb.run_batch_params(np.ascontiguousarray(P.T), ["Sentinel2A-MSI", "Sentinel2B-MSI"])
     assert relerr(hb, so.spart_bands(P, "Sentinel2B-MSI")) < RTOL64 and ha.shape == (5000, 13, 3)
+
+
+@pytest.mark.parametrize("sensor", ["Sentinel2A-MSI", "TerraAqua-MODIS", "LANDSAT8-OLI", "Sentinel3B-OLCI"])
+def test_smac_stage(env, sensor):
+    """SMAC alone against the oracle's restatement of smac.py:14-213 (nine AtmosphericOptics arrays;
+    float32 Sentinel-2 coefficients keep their NumPy dtype semantics)."""
+    _, sb, so = env
+    P = so.synthetic_params(3000, 3, seed=71)
+    P[:4, so.SZA], P[:4, so.VZA] = 0.0, 0.0                       # cksi clamp boundary (smac.py:134-135)
+    want = so.smac(P[:, so.SZA:so.RAA + 1], P[:, so.AOT550:so.PA + 1], so.load_sensor(sensor)["SMAC_coef"])
+    got = sb.smac_batch(P[:, so.SZA:so.RAA + 1], P[:, so.AOT550:so.PA + 1], sensor)
+    for i, k in enumerate(sb.stages.ATM_FIELDS):
+        assert relerr(got[:, i], np.broadcast_to(want[k], got[:, i].shape)) < RTOL64, k
+    one = sb.SMAC(sb.Angles(*P[7, so.SZA:so.RAA + 1]), sb.AtmosphericProperties(*P[7, so.AOT550:so.PA + 1]), sensor)
+    assert one.Tg.shape == (1, got.shape[2]) and np.array_equal(one.Ra_so[0], got[7, 4])
