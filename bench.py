@@ -207,6 +207,15 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # keep this rank (and the pinned host buffers it first-touches) on the CPUs next to its GPU;
+    # the original affinity is restored before the CPU baseline leg
+    full_affinity = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+    except Exception:
+        pass
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -335,6 +344,8 @@ def run_ours(args):
         roofline["traffic"] = roofline_hbm["traffic"] = t.get(dominant)
 
     # --- CPU baseline: the oracle port on all host cores, bounded sample -----------------
+    if full_affinity is not None:
+        os.sched_setaffinity(0, full_affinity)
     cores = host_cores()
     cpu = None
     if not args.no_cpu:

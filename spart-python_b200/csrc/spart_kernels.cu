@@ -156,6 +156,9 @@ constexpr int kLidfSpw = SPART_LIDF_SPW;
 #ifndef SPART_LIDF_BSTEPS
 #define SPART_LIDF_BSTEPS 16     // polynomial steps per bookkeeping round
 #endif
+#ifndef SPART_LIDF_BLOOP
+#define SPART_LIDF_BLOOP 0
+#endif
 #ifndef SPART_LIDF_BATCH_B
 #define SPART_LIDF_BATCH_B 8     // idle lanes that trigger a stage-B hand-out (its set-up costs a sincos)
 #endif
@@ -247,6 +250,25 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
     bool running = false;
     int iters = 0;
     while (true) {
+#if SPART_LIDF_BLOOP
+      // up to SPART_LIDF_BSTEPS polynomial steps per bookkeeping round; converged lanes drop out of
+      // the loop (hardware divergence), so a step costs the 7 FMA, the difference and the test only
+      for (int rep = 0; rep < SPART_LIDF_BSTEPS && running; ++rep) {
+        double un = fma(g7, u, g6);
+        un = fma(un, u, g5);
+        un = fma(un, u, g4);
+        un = fma(un, u, g3);
+        un = fma(un, u, g2);
+        un = fma(un, u, g1);
+        un = fma(un, u, g0);
+        if (!(fabs(un - u) > 1e-8)) {
+          uf = u;
+          unf = un;
+          running = false;
+        }
+        u = un;
+      }
+#else
       // SPART_LIDF_BSTEPS polynomial steps per bookkeeping round, branch-free: a lane that
       // converges inside the round freezes (u, u_new) of its last step with selects
 #pragma unroll
@@ -265,6 +287,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
         u = running ? un : u;
         running = running && !stop;
       }
+#endif
       const unsigned idle = __ballot_sync(full, !running);
       const int nidle = __popc(idle);
       if (next < kLidfTasks) {
