@@ -20,7 +20,17 @@ namespace f32 {
 __constant__ float c_gl_xf[SPART_NQ] = SPART_GL12_X;
 __constant__ float c_gl_wf[SPART_NQ] = SPART_GL12_W;
 
-__device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+// SFU reciprocal / square root (1-2 ulp, no slow path)
+__device__ __forceinline__ float rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fsqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // 1 - e^z for z <= 0 without cancellation near z = 0
 __device__ __forceinline__ float one_minus_exp(float z) {
   if (fabsf(z) < 0.05f) return -z * (1.0f + z * (0.5f + z * (1.0f / 6.0f + z * (1.0f / 24.0f))));
@@ -114,7 +124,7 @@ __device__ __forceinline__ void prospect_point_f(const LeafParF& L, const float*
     Tsub = t * rcp(t + (1.0f - t) * Nm1);
     Rsub = 1.0f - Tsub;
   } else {
-    const float D = sqrtf((1.0f + r + t) * (1.0f + r - t) * (1.0f - r + t) * (1.0f - r - t));
+    const float D = fsqrt((1.0f + r + t) * (1.0f + r - t) * (1.0f - r + t) * (1.0f - r - t));
     const float rq = r * r, tq = t * t;
     const float a = (1.0f + rq - tq + D) * rcp(2.0f * r);
     const float b = (1.0f - rq + tq + D) * rcp(2.0f * t);
@@ -181,7 +191,7 @@ __device__ __forceinline__ void sailh_point_f(const CanopyGeoF& G, float rho, fl
   const float w = G.sob * rho + G.sof * tau;
   const float a = 1.0f - sigf;
   // a^2 - sigb^2 = (1 - rho - tau)(a + sigb): the first factor is formed directly (sigf + sigb = rho + tau)
-  const float m = sqrtf((1.0f - rho - tau) * (a + sigb));
+  const float m = fsqrt((1.0f - rho - tau) * (a + sigb));
   const float rinf = (a - m) * rcp(sigb);
   const float rinf2 = rinf * rinf;
   const float e1 = fexp(-m * LAI);
@@ -246,11 +256,11 @@ __device__ __forceinline__ void volscatt_class_f(float sin_tts, float cos_tts, f
   const float Cs = cos_ttli * cos_tts, Ss = sin_ttli * sin_tts;
   const float Co = cos_ttli * cos_tto, So = sin_ttli * sin_tto;
   const float As = fmaxf(Ss, Cs), Ao = fmaxf(So, Co);
-  const float cbs = -Cs / As, cbo = -Co / Ao;
+  const float cbs = -Cs / As, cbo = -Co / Ao;     // exact: the quotient must be exactly -1 when As == Cs
   const float bts = acosf(cbs), bto = acosf(cbo);
   // sin(acos z) = sqrt(1 - z^2)
-  chi_o = 2.0f / SPART_PI_F * ((bto - SPART_PI_F / 2.0f) * Co + sqrtf(fmaxf(0.0f, 1.0f - cbo * cbo)) * So);
-  chi_s = 2.0f / SPART_PI_F * ((bts - SPART_PI_F / 2.0f) * Cs + sqrtf(fmaxf(0.0f, 1.0f - cbs * cbs)) * Ss);
+  chi_o = 2.0f / SPART_PI_F * ((bto - SPART_PI_F / 2.0f) * Co + fsqrt(fmaxf(0.0f, 1.0f - cbo * cbo)) * So);
+  chi_s = 2.0f / SPART_PI_F * ((bts - SPART_PI_F / 2.0f) * Cs + fsqrt(fmaxf(0.0f, 1.0f - cbs * cbs)) * Ss);
   const float delta1 = fabsf(bts - bto);
   const float delta2 = SPART_PI_F - fabsf(bts + bto - SPART_PI_F);
   const float Tot = psi_rad + delta1 + delta2;
@@ -261,26 +271,26 @@ __device__ __forceinline__ void volscatt_class_f(float sin_tts, float cos_tts, f
   const float T2 = sinf(bt2) * (2.0f * As * Ao + Ss * So * cosf(bt1) * cosf(bt3));
   const float Jmin = bt2 * T1 - T2;
   const float Jplus = (SPART_PI_F - bt2) * T1 + T2;
-  frho = fmaxf(0.0f, Jplus / (2.0f * SPART_PI_F * SPART_PI_F));
-  ftau = fmaxf(0.0f, -Jmin / (2.0f * SPART_PI_F * SPART_PI_F));
+  frho = fmaxf(0.0f, Jplus * (1.0f / (2.0f * SPART_PI_F * SPART_PI_F)));
+  ftau = fmaxf(0.0f, -Jmin * (1.0f / (2.0f * SPART_PI_F * SPART_PI_F)));
 }
 
 // hot-spot integrals, see hotspot_integrals in spart_device.cuh (sailh.py:116-135, 216-219)
 __device__ __forceinline__ void hotspot_integrals_f(float K, float k, float LAI, float q, float dso,
                                                     float& sumpso_ilai, float& pso2w) {
   const float A0 = (K + k) * LAI;
-  const float S = sqrtf(K * k) * LAI;
+  const float S = fsqrt(K * k) * LAI;
   const float Amin = A0 - S;
   float A = A0, Cq = 0.0f, alpha = 0.0f;
   if (dso != 0.0f) {
-    alpha = (dso / q) * 2.0f / (k + K);
-    Cq = S / alpha;
+    alpha = (dso * rcp(q)) * 2.0f * rcp(k + K);
+    Cq = S * rcp(alpha);
   } else {
     A = Amin;
   }
   float L = 1.0f;
-  if (alpha > 0.0f) L = fminf(L, 20.0f / alpha);     // e^-20 = 2e-9 is below float resolution of the integral
-  if (Amin > 0.0f) L = fminf(L, 20.0f / Amin);
+  if (alpha > 0.0f) L = fminf(L, 20.0f * rcp(alpha));     // e^-20 = 2e-9 is below float resolution of the integral
+  if (Amin > 0.0f) L = fminf(L, 20.0f * rcp(Amin));
   const int NP = 4;      // alpha h <= 5, A h <= 10: far inside what a 12-point rule resolves to 1e-7
   const float h = L * (1.0f / NP);
   float total = 0.0f;
@@ -297,7 +307,7 @@ __device__ __forceinline__ void hotspot_integrals_f(float K, float k, float LAI,
     total += acc;
   }
   total *= 0.5f * h;
-  if (L < 1.0f && alpha * L >= 20.0f * (1.0f - 1e-6f)) total += fexp(Cq - A * L) * (1.0f - fexp(-A * (1.0f - L))) / A;
+  if (L < 1.0f && alpha * L >= 20.0f * (1.0f - 1e-6f)) total += fexp(Cq - A * L) * (1.0f - fexp(-A * (1.0f - L))) * rcp(A);
   sumpso_ilai = total * LAI;
   const float dx = 1.0f / 60.0f;
   const float xc = -1.0f - 0.5f * dx;

@@ -775,11 +775,11 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
   float sin_tts, cos_tts, sin_tto, cos_tto;
   sincosf(tts * (SPART_PI_F / 180.0f), &sin_tts, &cos_tts);
   sincosf(tto * (SPART_PI_F / 180.0f), &sin_tto, &cos_tto);
-  const float tan_tts = sin_tts / cos_tts, tan_tto = sin_tto / cos_tto;
+  const float inv_cs = rcp(cos_tts), inv_co = rcp(cos_tto);
+  const float tan_tts = sin_tts * inv_cs, tan_tto = sin_tto * inv_co;
   const float cos_psi = cosf(psi_rad);
-  const float dso = sqrtf(fmaxf(0.0f, tan_tts * tan_tts + tan_tto * tan_tto - 2.0f * tan_tts * tan_tto * cos_psi));
-  const float inv_cc = SPART_PI_F / (cos_tts * cos_tto);
-  const float inv_cs = 1.0f / cos_tts, inv_co = 1.0f / cos_tto;
+  const float dso = fsqrt(fmaxf(0.0f, tan_tts * tan_tts + tan_tto * tan_tto - 2.0f * tan_tts * tan_tto * cos_psi));
+  const float inv_cc = SPART_PI_F * inv_cs * inv_co;
 
   if (uniform_geometry) {
     if (tid < 13) {
@@ -832,7 +832,7 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
   rec[R_TAUOO * n + s] = tau_oo;
   rec[R_SUMPSO * n + s] = sumpso;
   rec[R_PSO2W * n + s] = pso2w;
-  rec[R_Z * n + s] = one_minus_exp(-(k + K) * LAI) / (K + k);
+  rec[R_Z * n + s] = one_minus_exp(-(k + K) * LAI) * rcp(K + k);
 
   {
     const float B = (float)P[P_B * ld + s];
@@ -857,7 +857,8 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
     if (cksi < -1.0) cksi = -1.0;
     const float us = (float)us_d, uv = (float)uv_d;
     const float Peq = (float)(P[P_PA * ld + s] / 1013.25);
-    const float m = 1.0f / us + 1.0f / uv;
+    const float inv_us = rcp(us), inv_uv = rcp(uv);
+    const float m = inv_us + inv_uv;
     rec[R_US * n + s] = us;
     rec[R_UV * n + s] = uv;
     rec[R_M * n + s] = m;
@@ -869,11 +870,11 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
     rec[R_CKSI * n + s] = (float)cksi;
     rec[R_KSID * n + s] = (float)(crd * acos(cksi));
     rec[R_RAYPH * n + s] = (float)(0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742);
-    rec[R_INVUS * n + s] = 1.0f / us;
-    rec[R_INVUV * n + s] = 1.0f / uv;
-    rec[R_INV1PUS * n + s] = 1.0f / (1.0f + us);
-    rec[R_INV1PUV * n + s] = 1.0f / (1.0f + uv);
-    rec[R_AA3 * n + s] = us * uv / (us + uv);
+    rec[R_INVUS * n + s] = inv_us;
+    rec[R_INVUV * n + s] = inv_uv;
+    rec[R_INV1PUS * n + s] = rcp(1.0f + us);
+    rec[R_INV1PUV * n + s] = rcp(1.0f + uv);
+    rec[R_AA3 * n + s] = us * uv * rcp(us + uv);
     const float bb = 2.0f * SPART_PI_F * (float)P[P_DOY * ld + s] / 365.0f;
     float sb, cb, s2b, c2b;
     sincosf(bb, &sb, &cb);
