@@ -8,8 +8,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "csrc" / "spart_kernels.cu"
-DEPS = [SRC, HERE / "csrc" / "spart_device.cuh", HERE / "csrc" / "tau_coeffs.h",
-        HERE.parent / "include" / "spart_b200.h"]
+DEPS = sorted((HERE / "csrc").glob("*")) + [HERE.parent / "include" / "spart_b200.h"]
 OUT = HERE / "spart_b200" / "lib" / "libspart_b200.so"
 
 NVCC_FLAGS = [

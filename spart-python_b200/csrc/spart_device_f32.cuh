@@ -226,6 +226,18 @@ __device__ __forceinline__ void sailh_point_f(const CanopyGeoF& G, float rho, fl
   rdd = rho_dd + tau_dd * tau_dd * rs_den;
 }
 
+// sin / cos for |x| up to a few pi: fold to [-pi/2, pi/2] and use the SFU sine / cosine there
+// (absolute error ~4e-7), which is what the Newton solve below needs
+__device__ __forceinline__ void sincos_sfu(float x, float& s, float& c) {
+  const float kf = rintf(x * (1.0f / SPART_PI_F));
+  float r = fmaf(-kf, 3.140625f, x);                    // pi = 3.140625 + 9.67653589793e-4 (Cody-Waite)
+  r = fmaf(-kf, 9.67653589793e-4f, r);
+  const int odd = ((int)kf) & 1;
+  const float s0 = __sinf(r), c0 = __cosf(r);
+  s = odd ? -s0 : s0;
+  c = odd ? -c0 : c0;
+}
+
 // Cumulative leaf-angle value F(theta) = (2 y(x*) + theta2) / pi with x* the root of
 // y(x) - x + theta2 = 0, y = a sin x + b/2 sin 2x (the fixed point of sailh.py:378-382).
 // y - x is monotone decreasing for |a| + |b| <= 1, so Newton is safeguarded by the bracket
@@ -236,7 +248,7 @@ __device__ __forceinline__ float dcum_newton_f(float a, float b, float theta2) {
 #pragma unroll 1
   for (int it = 0; it < 6; ++it) {
     float s, c;
-    sincosf(x, &s, &c);
+    sincos_sfu(x, s, c);
     const float f = s * fmaf(b, c, a) - x + theta2;
     const float fp = fmaf(a, c, b * (2.0f * c * c - 1.0f)) - 1.0f;
     lo = (f > 0.0f) ? x : lo;
@@ -245,7 +257,7 @@ __device__ __forceinline__ float dcum_newton_f(float a, float b, float theta2) {
     x = (xn >= lo && xn <= hi) ? xn : 0.5f * (lo + hi);
   }
   float s, c;
-  sincosf(x, &s, &c);
+  sincos_sfu(x, s, c);
   return (2.0f * s * fmaf(b, c, a) + theta2) * (1.0f / SPART_PI_F);
 }
 
