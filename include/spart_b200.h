@@ -179,6 +179,17 @@ int spart_sailh(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_
  * out_dev: double [n][13].  Needs no context. */
 int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_dev, void* stream);
 
+/* Consumer of a LUT (new; the reference has no retrieval step): for each of m observed band
+ * vectors obs_dev [m][n_bands] (float) the index of the LUT entry lut_dev [n][n_bands] (float, e.g.
+ * one output column of spart_forward_bands cast to float) with the smallest weighted squared
+ * distance sum_b (sqrt_w[b] (obs_b - lut_b))^2, ties to the lowest index.  weights_dev: sqrt of the
+ * band weights [n_bands] or NULL (all 1).  workspace_dev: spart_lut_workspace_bytes(m) bytes.
+ * Outputs best_index_dev int32 [m], best_cost_dev float [m]. */
+size_t spart_lut_workspace_bytes(int64_t m);
+int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const float* obs_dev, int64_t m,
+                      const float* weights_dev, void* workspace_dev, int32_t* best_index_dev,
+                      float* best_cost_dev, void* stream);
+
 /* Per-kernel timing of spart_forward_bands with CUDA events recorded on the caller's stream
  * (used by bench.py for the roofline).  After spart_profile_enable(ctx, 1) every
  * spart_forward_bands call records events around its SPART_NKERNELS kernels; spart_profile_read

@@ -25,6 +25,7 @@
 #include "../../include/spart_b200.h"
 #include "spart_device.cuh"
 #include "spart_device_f32.cuh"
+#include "lut_kernels.cuh"
 
 using namespace spart;
 
@@ -1401,6 +1402,51 @@ int spart_sailh(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
   }
+  return SPART_OK;
+}
+
+size_t spart_lut_workspace_bytes(int64_t m) { return m > 0 ? sizeof(unsigned long long) * (size_t)m : 0; }
+
+int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const float* obs_dev, int64_t m,
+                      const float* weights_dev, void* workspace_dev, int32_t* best_index_dev, float* best_cost_dev,
+                      void* stream) {
+  if (!lut_dev || !obs_dev || !best_index_dev || !best_cost_dev || (!workspace_dev && m > 0))
+    return fail(SPART_EINVAL, "spart_lut_nearest: null argument%s");
+  if (n <= 0 || n > 0x7fffffffLL || m < 0 || n_bands < 1 || n_bands > 32)
+    return fail(SPART_EINVAL, "spart_lut_nearest: need 1 <= n < 2^31, m >= 0, 1 <= n_bands <= 32%s");
+  if (m == 0) return SPART_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* best = (unsigned long long*)workspace_dev;
+  CUDA_TRY(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * m, st));
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t obs_blocks = (m + kLutObs - 1) / kLutObs;
+  // enough LUT slices that the grid fills the GPU a few times over, each slice a whole number of tiles
+  int64_t slices = (8LL * sms + obs_blocks - 1) / obs_blocks;
+  const int64_t max_slices = (n + kLutTile - 1) / kLutTile;
+  if (slices > max_slices) slices = max_slices;
+  if (slices > 65535) slices = 65535;
+  if (slices < 1) slices = 1;
+  int64_t per_slice = (n + slices - 1) / slices;
+  per_slice = ((per_slice + kLutTile - 1) / kLutTile) * kLutTile;
+  slices = (n + per_slice - 1) / per_slice;
+  dim3 grid((unsigned)obs_blocks, (unsigned)slices);
+  const int nb4 = (n_bands + 3) / 4;
+#define SPART_LUT_CASE(K)                                                                                          \
+  case K:                                                                                                          \
+    lut_nearest_kernel<K><<<grid, kLutObs, 0, st>>>(lut_dev, n, n_bands, obs_dev, m, weights_dev, per_slice, best); \
+    break;
+  switch (nb4) {
+    SPART_LUT_CASE(1) SPART_LUT_CASE(2) SPART_LUT_CASE(3) SPART_LUT_CASE(4)
+    SPART_LUT_CASE(5) SPART_LUT_CASE(6) SPART_LUT_CASE(7) SPART_LUT_CASE(8)
+  }
+#undef SPART_LUT_CASE
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  lut_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(best, m, best_index_dev, best_cost_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
   return SPART_OK;
 }
 

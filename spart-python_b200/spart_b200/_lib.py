@@ -25,7 +25,7 @@ FP32 = 32
 EXPORTS = (
     "spart_abi_version", "spart_last_error", "spart_device_count", "spart_create", "spart_destroy",
     "spart_workspace_bytes", "spart_forward_bands", "spart_forward_bands_host", "spart_forward_spectrum",
-    "spart_smac", "spart_sailh", "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
+    "spart_smac", "spart_sailh", "spart_lut_workspace_bytes", "spart_lut_nearest", "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
 )
 
 
@@ -80,6 +80,10 @@ def load():
     lib.spart_smac.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.spart_sailh.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                 c_void_p, c_void_p]
+    lib.spart_lut_workspace_bytes.argtypes = [c_int64]
+    lib.spart_lut_workspace_bytes.restype = c_size_t
+    lib.spart_lut_nearest.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]
     lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]

@@ -1,0 +1,56 @@
+"""Look-up-table helpers: generation in chunks and nearest-entry retrieval on the GPU.
+
+`generate` runs a parameter block through the forward model chunk by chunk (bounded device
+memory) and returns / stores the band outputs; `nearest` is the retrieval step: the LUT entry with
+the smallest weighted squared distance to each observed band vector (spart_lut_nearest).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import default_engine
+
+
+def generate(params, sensor, precision="fp64", chunk=1 << 20, out_dtype=torch.float32, column=None, path=None,
+             uniform_geometry=False):
+    """params: [27, n] (NumPy or torch, host or device).  Evaluates the batch in chunks of `chunk`
+    samples and returns a CUDA tensor [n, nb, 3] (or [n, nb] when `column` selects 0 = R_TOC,
+    1 = R_TOA, 2 = L_TOA) in `out_dtype`.  With `path` the table is also written as a compressed
+    .npz holding `params` [n, 27] float32 and `lut`."""
+    eng = default_engine()
+    p = params if isinstance(params, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(params))
+    n = p.shape[1]
+    _, st = eng.sensor(sensor)
+    shape = (n, st.n_bands) if column is not None else (n, st.n_bands, 3)
+    lut = torch.empty(shape, dtype=out_dtype, device=eng.device)
+    for s0 in range(0, n, chunk):
+        blk = p[:, s0:s0 + chunk].to(eng.device, dtype=torch.float64).contiguous()
+        res = eng.forward_bands(blk, sensor, precision=precision, uniform_geometry=uniform_geometry)
+        lut[s0:s0 + chunk] = (res[..., column] if column is not None else res).to(out_dtype)
+    if path is not None:
+        np.savez_compressed(path, params=p.T.to(torch.float32).cpu().numpy(), lut=lut.cpu().numpy(),
+                            sensor=np.array(sensor if isinstance(sensor, str) else "custom"))
+    return lut
+
+
+def nearest(lut, obs, weights=None):
+    """lut: CUDA float32 [n, nb]; obs: CUDA float32 [m, nb]; weights: optional per-band weights [nb].
+    Returns (index int64 [m], cost float32 [m]) of the entry minimising sum_b w_b (obs_b - lut_b)^2."""
+    lib = _lib.load()
+    if not (lut.is_cuda and obs.is_cuda and lut.dtype == torch.float32 and obs.dtype == torch.float32
+            and lut.dim() == 2 and obs.dim() == 2 and lut.shape[1] == obs.shape[1]):
+        raise ValueError("lut [n, nb] and obs [m, nb] must be CUDA float32 tensors with the same band count")
+    lut, obs = lut.contiguous(), obs.contiguous()
+    n, nb = lut.shape
+    m = obs.shape[0]
+    w = None
+    if weights is not None:
+        w = torch.as_tensor(weights, dtype=torch.float32, device=lut.device).reshape(nb).clamp_min(0).sqrt().contiguous()
+    idx = torch.empty(m, dtype=torch.int32, device=lut.device)
+    cost = torch.empty(m, dtype=torch.float32, device=lut.device)
+    ws = torch.empty(max(lib.spart_lut_workspace_bytes(m) // 8, 1), dtype=torch.int64, device=lut.device)
+    stream = torch.cuda.current_stream(lut.device).cuda_stream
+    with torch.cuda.device(lut.device):
+        _lib.check(lib.spart_lut_nearest(lut.data_ptr(), n, nb, obs.data_ptr(), m, 0 if w is None else w.data_ptr(),
+                                         ws.data_ptr(), idx.data_ptr(), cost.data_ptr(), stream), "spart_lut_nearest")
+    return idx.to(torch.int64), cost

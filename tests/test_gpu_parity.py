@@ -393,3 +393,32 @@ def test_smac_stage(env, sensor):
         assert relerr(got[:, i], np.broadcast_to(want[k], got[:, i].shape)) < RTOL64, k
     one = sb.SMAC(sb.Angles(*P[7, so.SZA:so.RAA + 1]), sb.AtmosphericProperties(*P[7, so.AOT550:so.PA + 1]), sensor)
     assert one.Tg.shape == (1, got.shape[2]) and np.array_equal(one.Ra_so[0], got[7, 4])
+
+
+def test_lut_generate_and_nearest(env, tmp_path):
+    """LUT consumer: chunked generation and nearest-entry retrieval against a brute-force search."""
+    torch, sb, so = env
+    P = so.synthetic_params(6000, 2, seed=91)
+    lut = sb.lut.generate(P.T, "Sentinel2A-MSI", column=0, chunk=2500, path=str(tmp_path / "lut.npz"),
+                          uniform_geometry=True)
+    assert lut.shape == (6000, 13) and lut.dtype == torch.float32
+    want = so.spart_bands(P[:200], "Sentinel2A-MSI")[:, :, 0]
+    assert relerr(lut[:200].cpu().numpy(), want) < 1e-6                       # float32 storage
+    z = np.load(tmp_path / "lut.npz")
+    assert z["lut"].shape == (6000, 13) and z["params"].shape == (6000, 27)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for nb, n, m in ((13, 6000, 777), (26, 5000, 300), (6, 333, 1000), (1, 100, 5)):
+        L = torch.rand((n, nb), generator=g, device="cuda", dtype=torch.float32)
+        O = torch.rand((m, nb), generator=g, device="cuda", dtype=torch.float32)
+        w = torch.rand(nb, generator=g, device="cuda", dtype=torch.float32) + 0.1
+        for weights in (None, w):
+            idx, cost = sb.lut.nearest(L, O, weights)
+            ww = torch.ones(nb, device="cuda") if weights is None else weights
+            d = ((O[:, None, :].double() - L[None, :, :].double()) ** 2 * ww.double()).sum(-1)
+            best = d.min(dim=1)
+            # the chosen entry is optimal up to float rounding of the cost
+            assert torch.all(d.gather(1, idx[:, None])[:, 0] <= best.values * (1 + 1e-5) + 1e-12)
+            assert torch.allclose(cost.double(), best.values, rtol=1e-4, atol=1e-9)
+    # an observation that is a LUT row finds itself; retrieval of noisy simulations finds a near neighbour
+    idx, cost = sb.lut.nearest(lut, lut[100:164].clone())
+    assert torch.equal(idx.cpu(), torch.arange(100, 164)) and float(cost.max()) == 0.0

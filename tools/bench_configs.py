@@ -81,4 +81,13 @@ outsp = torch.empty((nspec, 9, 2162), dtype=torch.float64, device=dev)
 r = timed(lambda: eng.forward_spectrum(Psp, out=outsp), nspec)
 r["output_gb_per_s"] = nspec * 9 * 2162 * 8 / (r["ms_per_step"] * 1e-3) / 1e9
 res["canopyopt_spectra_9x2162_fp64"] = r
+# retrieval: nearest LUT entry for 100k observations against a 1M-entry Sentinel-2A LUT
+g = torch.Generator(device=dev).manual_seed(3)
+L = torch.rand((1_000_000, 13), generator=g, device=dev, dtype=torch.float32)
+O = torch.rand((100_000, 13), generator=g, device=dev, dtype=torch.float32)
+r = timed(lambda: spart_b200.lut.nearest(L, O), 100_000)
+pairs = 1e6 * 1e5
+r["pairs_per_s"] = pairs / (r["ms_per_step"] * 1e-3)
+r["fp32_tflops"] = pairs * 13 * 3 / (r["ms_per_step"] * 1e-3) / 1e12      # sub + fma per band
+res["lut_nearest_100k_obs_x_1M_entries_13_bands"] = r
 print(json.dumps(res, indent=1))
