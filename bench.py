@@ -49,14 +49,31 @@ BYTES_PER_SAMPLE = {"lidf_kernel": (2 + 12) * 8, "geometry_kernel": (12 + 12 + 3
 
 
 def kernel_source_sha():
-    """Hash of the CUDA sources: the executed-flop counts in profiles/flop_per_sample.json are only
-    valid for the kernel build they were measured on."""
+    """Identity of the build the executed-flop counts in profiles/flop_per_sample.json belong to: a
+    hash of the SASS of the three band-path kernels (so that adding or editing unrelated kernels does
+    not invalidate the counts); falls back to a hash of the CUDA sources without cuobjdump."""
     import hashlib
+    import re
+    import shutil
+    import subprocess
     h = hashlib.sha256()
-    for f in sorted((ROOT / "spart-python_b200" / "csrc").glob("*")):
-        if f.suffix in (".cu", ".cuh", ".h"):
-            h.update(f.read_bytes())
-    return h.hexdigest()[:16]
+    lib = ROOT / "spart-python_b200" / "spart_b200" / "lib" / "libspart_b200.so"
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    try:
+        txt = subprocess.run([cuobjdump, "-sass", str(lib)], capture_output=True, text=True, check=True).stdout
+        keep = False
+        for line in txt.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                keep = bool(re.search(r"lidf_kernel|geometry_kernelPK|band_kernelPK", m.group(1)))
+            if keep:
+                h.update(re.sub(r"/\*[0-9a-f]{16}\*/", "", line).encode())     # drop the encoding column
+        return "sass:" + h.hexdigest()[:16]
+    except Exception:
+        for f in sorted((ROOT / "spart-python_b200" / "csrc").glob("*")):
+            if f.suffix in (".cu", ".cuh", ".h"):
+                h.update(f.read_bytes())
+        return "src:" + h.hexdigest()[:16]
 
 
 def load_flop_counts():

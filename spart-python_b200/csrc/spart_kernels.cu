@@ -29,7 +29,7 @@
 
 using namespace spart;
 
-// tuning knobs (tools/tune_variants.sh builds alternatives)
+// tuning knobs: build alternatives with -D... and time them with SPART_B200_LIB=<so> python tools/kbench.py
 #ifndef SPART_BAND_CHUNK
 #define SPART_BAND_CHUNK 16
 #endif
