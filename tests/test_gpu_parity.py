@@ -422,3 +422,37 @@ def test_lut_generate_and_nearest(env, tmp_path):
     # an observation that is a LUT row finds itself; retrieval of noisy simulations finds a near neighbour
     idx, cost = sb.lut.nearest(lut, lut[100:164].clone())
     assert torch.equal(idx.cpu(), torch.arange(100, 164)) and float(cost.max()) == 0.0
+
+
+def test_spart_class_api_details(env):
+    """Drop-in details of SPART(...).run() (SPART.py:254-269): column order, Band labels, index
+    dtype per sensor, debug column, mutable parameter attributes, custom sensorinfo dicts."""
+    torch, sb, so = env
+    args = lambda: (sb.SoilParameters(0.5, 0, 100, 20, 25, 0.015), sb.LeafBiology(40, 0.01, 0.02, 0, 10, 10, 1.5),
+                    sb.CanopyStructure(3, -0.35, -0.15, 0.05), sb.AtmosphericProperties(0.325, 0.35, 1.41),
+                    sb.Angles(40, 0, 0))
+    s2 = sb.SPART(*args(), "Sentinel2A-MSI", 100)
+    df = s2.run(debug=True)
+    assert list(df.columns) == ["Band", "L_TOA", "R_TOA", "R_TOC", "rsoil"]
+    assert df.index.dtype == np.uint16 and list(df["Band"]) == [""] * 13          # as in the reference's pickle
+    assert s2.R_TOC.shape == (1, 13) and s2.L_TOA.shape == (1, 13)
+    assert s2.canopyopt.rso.shape == (2162, 1) and s2.leafopt.kChlrel.shape == (2001, 1)
+    assert np.allclose(df["rsoil"].to_numpy(), np.interp(df.index.to_numpy(), s2.spectral.wlS, s2.soilopt.refl[:, 0]))
+    modis = sb.SPART(*args(), "TerraAqua-MODIS", 100).run()
+    assert modis.index.dtype == np.float64 and modis["Band"].iloc[0].startswith("Band")
+    # parameters are plain mutable attributes; every run() is a fresh evaluation (no stale-SMAC bug)
+    before = s2.run()["R_TOA"].to_numpy().copy()
+    s2.angles = sb.Angles(30, 10, 90)
+    after = s2.run()["R_TOA"].to_numpy()
+    fresh = sb.SPART(*args()[:4], sb.Angles(30, 10, 90), "Sentinel2A-MSI", 100).run()["R_TOA"].to_numpy()
+    assert not np.allclose(before, after) and np.array_equal(after, fresh)
+    # a user-assigned sensorinfo dict (the reference's attribute is plain, SPART.py:95)
+    custom = sb.SPART(*args(), "TerraAqua-MODIS", 100)
+    custom.sensorinfo = sb.synthetic_fullspectrum_sensorinfo()
+    out = custom.run()
+    assert len(out) == 2001 and np.isfinite(out["R_TOC"].to_numpy()).all()
+    with pytest.raises(FileNotFoundError):
+        sb.SPART(*args(), "NoSuchSensor", 100)
+    row = sb.row_as_dataframe(torch.from_numpy(np.stack([df["R_TOC"], df["R_TOA"], df["L_TOA"]], axis=1)),
+                              "Sentinel2A-MSI")
+    assert np.array_equal(row["L_TOA"].to_numpy(), df["L_TOA"].to_numpy())
