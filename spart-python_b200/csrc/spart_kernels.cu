@@ -8,7 +8,7 @@
 //        vector weights, SMAC geometry/pressure scalars, ET scale)
 //   params + rec    --band_kernel---->  out [n][nb][3]      (one thread per (sample, band):
 //        PROSPECT + BSM + SAILH at the 1-2 wavelengths np.interp touches, SMAC, TOC->TOA)
-//   params + rec    --spectrum_kernel-> spec [n][9][2162]   (leafopt/soilopt/canopyopt)
+//   params + rec    --spectrum_kernel-> spec [n][9][2162]   (leafopt/soilopt/canopyopt; thread = wavelength)
 //
 // In band_kernel / spectrum_kernel all lanes of a warp work on the same wavelength, so the
 // per-wavelength and per-band constants are warp-uniform shared-memory broadcasts and the
@@ -950,52 +950,48 @@ band_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, const float
   }
 }
 
-// Full-spectrum planes: blockIdx.x = chunk of kSpecChunk wavelengths, blockIdx.y = sample tile.
-constexpr int kSpecThreads = 128;
-constexpr int kSpecChunk = 32;
+// Full-spectrum planes (leafopt / soilopt / canopyopt): thread = wavelength, blockIdx.y = sample.
+// Every load of the per-wavelength constants and every store of the nine output planes is then
+// coalesced along the wavelength axis (the output is 155 KB per sample, so this kernel lives on
+// its store pattern); the sample's parameters and record are warp-uniform broadcast loads.
+constexpr int kSpecThreads = 256;
 
 __global__ void __launch_bounds__(kSpecThreads)
 spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
-                const double* __restrict__ lc_table, double* __restrict__ out) {
+                const double* __restrict__ lc_table, int64_t s0, double* __restrict__ out) {
   __shared__ TauTable s_tau;
-  __shared__ double s_lc[kSpecChunk][LC_COUNT];
-  const int w0 = blockIdx.x * kSpecChunk;
   load_tau_table(&s_tau);
-  for (int i = threadIdx.x; i < kSpecChunk * LC_COUNT; i += blockDim.x) {
-    const int w = w0 + i / LC_COUNT, r = i % LC_COUNT;
-    // thermal wavelengths re-use the 2400 nm soil constants (SPART.py:440)
-    s_lc[i / LC_COUNT][r] = lc_table[(size_t)r * SPART_NWL + min(w, SPART_NWL - 1)];
-  }
   __syncthreads();
-  const int64_t s = (int64_t)blockIdx.y * kSpecThreads + threadIdx.x;
-  if (s >= n) return;
+  const int w = blockIdx.x * kSpecThreads + threadIdx.x;
+  const int64_t s = s0 + blockIdx.y;
+  if (w >= SPART_NWL_S || s >= n) return;
   const LeafPar L = load_leaf(P, ld, s);
   const SoilPar S = load_soil(P, ld, rec, n, s);
   const CanopyGeo G = load_geo(P, ld, rec, n, s);
-  double* o = out + (size_t)s * SPART_NSPEC * SPART_NWL_S;
-  for (int j = 0; j < kSpecChunk; ++j) {
-    const int w = w0 + j;
-    if (w >= SPART_NWL_S) break;
-    double refl, tran, kchl, rwet, rdry, rso, rdo, rsd, rdd;
-    bsm_point(S, s_lc[j], rwet, rdry);
-    if (w < SPART_NWL) {
-      prospect_point<true>(L, s_lc[j], &s_tau, refl, tran, kchl);
-    } else {  // thermal assumptions (SPART.py:461-466; LeafBiology rho/tau_thermal = 0.01)
-      refl = 0.01;
-      tran = 0.01;
-      kchl = 0.0;
-    }
-    sailh_point(G, refl, tran, rwet, rso, rdo, rsd, rdd);
-    o[0 * SPART_NWL_S + w] = refl;
-    o[1 * SPART_NWL_S + w] = tran;
-    o[2 * SPART_NWL_S + w] = kchl;
-    o[3 * SPART_NWL_S + w] = rwet;
-    o[4 * SPART_NWL_S + w] = rdry;
-    o[5 * SPART_NWL_S + w] = rso;
-    o[6 * SPART_NWL_S + w] = rdo;
-    o[7 * SPART_NWL_S + w] = rsd;
-    o[8 * SPART_NWL_S + w] = rdd;
+  double lc[LC_COUNT];
+  const int wc = min(w, SPART_NWL - 1);     // thermal wavelengths re-use the 2400 nm soil constants (SPART.py:440)
+#pragma unroll
+  for (int r = 0; r < LC_COUNT; ++r) lc[r] = lc_table[(size_t)r * SPART_NWL + wc];
+  double refl, tran, kchl, rwet, rdry, rso, rdo, rsd, rdd;
+  bsm_point(S, lc, rwet, rdry);
+  if (w < SPART_NWL) {
+    prospect_point<true>(L, lc, &s_tau, refl, tran, kchl);
+  } else {  // thermal assumptions (SPART.py:461-466; LeafBiology rho/tau_thermal = 0.01)
+    refl = 0.01;
+    tran = 0.01;
+    kchl = 0.0;
   }
+  sailh_point(G, refl, tran, rwet, rso, rdo, rsd, rdd);
+  double* o = out + (size_t)s * SPART_NSPEC * SPART_NWL_S + w;
+  o[0 * SPART_NWL_S] = refl;
+  o[1 * SPART_NWL_S] = tran;
+  o[2 * SPART_NWL_S] = kchl;
+  o[3 * SPART_NWL_S] = rwet;
+  o[4 * SPART_NWL_S] = rdry;
+  o[5 * SPART_NWL_S] = rso;
+  o[6 * SPART_NWL_S] = rdo;
+  o[7 * SPART_NWL_S] = rsd;
+  o[8 * SPART_NWL_S] = rdd;
 }
 
 // ---- peak micro-benchmarks ---------------------------------------------------------------
@@ -1352,10 +1348,13 @@ int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_
   if (rc) return rc;
   rc = launch_geometry(params_dev, n, ld, rec, flags & ~SPART_FLAG_UNIFORM_GEOMETRY, st);
   if (rc) return rc;
-  dim3 grid((SPART_NWL_S + kSpecChunk - 1) / kSpecChunk, (unsigned)((n + kSpecThreads - 1) / kSpecThreads));
-  spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, out_dev);
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
+  for (int64_t s0 = 0; s0 < n; s0 += 65535) {
+    const unsigned ny = (unsigned)((n - s0 < 65535) ? (n - s0) : 65535);
+    dim3 grid((SPART_NWL_S + kSpecThreads - 1) / kSpecThreads, ny);
+    spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, s0, out_dev);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
   return SPART_OK;
 }
 
