@@ -85,6 +85,10 @@ __constant__ double c_tau_invhalf[SPART_TAU_NINT];
 #define SPART_NQ 12
 __constant__ double c_gl_x[SPART_NQ] = SPART_GL12_X;
 __constant__ double c_gl_w[SPART_NQ] = SPART_GL12_W;
+// 24-point rule for the two wide panels of the hot-spot integral
+#define SPART_NQ2 24
+__constant__ double c_gl24_x[SPART_NQ2] = SPART_GL24_X;
+__constant__ double c_gl24_w[SPART_NQ2] = SPART_GL24_W;
 
 // ---- bounded-range sine / cosine ------------------------------------------------------------
 // |x| is at most a few pi here (leaf-angle iteration), so a two-term Cody-Waite reduction by
@@ -563,11 +567,12 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
 // Here the first integral is split at x = -L, L = min(1, 40/alpha, 40/(A - sqrt(Kk) LAI)):
 //   * below -L either e^{alpha x} < e^-40 (pso is a pure exponential, integrated in closed
 //     form) or pso itself is < e^-40 of its peak (dropped);
-//   * [-L, 0] is covered by SPART_NP panels of a 12-point Gauss-Legendre rule; on every panel
-//     the exponent varies by at most ~4 and the e^{alpha x} kink by at most e^4, for which
-//     the rule is accurate to ~1e-14 (tools/check notes in DESIGN.md).
-// All lanes run the same trip counts (no divergence); cost 142 exp instead of 557.
-#define SPART_NP 10
+//   * [-L, 0] is covered by SPART_NP = 2 panels of a 24-point Gauss-Legendre rule.  The
+//     integrand is analytic; on a panel its exponent varies by at most ~40 and the high-order
+//     rule resolves it to ~4e-15 (tools/check notes in DESIGN.md: 2 x 24 nodes are as accurate
+//     as 10 x 12 or the reference's 60 x 21).
+// All lanes run the same trip counts (no divergence); cost 96 + 25 exp instead of 557.
+#define SPART_NP 2
 __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI, double q, double dso,
                                                   double& sumpso_ilai, double& pso2w) {
   const double A0 = (K + k) * LAI;
@@ -584,21 +589,17 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
   if (alpha > 0.0) L = fmin(L, 40.0 * rcp_fast(alpha));
   if (Amin > 0.0) L = fmin(L, 40.0 * rcp_fast(Amin));
   const double h = L * (1.0 / SPART_NP);
-  const double ah = alpha * h;
-  double gnode[SPART_NQ];
-#pragma unroll
-  for (int i = 0; i < SPART_NQ; ++i) gnode[i] = exp_bounded((0.5 * ah) * c_gl_x[i]);   // |arg| <= 2
   double total = 0.0;
 #pragma unroll 1
   for (int j = 0; j < SPART_NP; ++j) {
     const double xc = -(j + 0.5) * h;          // panel centre
-    const double ej = exp_bounded(alpha * xc);            // arg in [-40, 0]
     double acc = 0.0;
-#pragma unroll
-    for (int i = 0; i < SPART_NQ; ++i) {
-      const double x = fma(0.5 * h, c_gl_x[i], xc);
-      const double arg = fma(A, x, Cq * (1.0 - ej * gnode[i]));
-      acc = fma(c_gl_w[i], exp_bounded(arg), acc);       // arg in [-80, 0]: A L <= 40 A / Amin <= 80
+#pragma unroll 4
+    for (int i = 0; i < SPART_NQ2; ++i) {
+      const double x = fma(0.5 * h, c_gl24_x[i], xc);
+      const double ea = exp_bounded(alpha * x);                 // alpha x in [-40, 0]
+      const double arg = fma(A, x, Cq * (1.0 - ea));
+      acc = fma(c_gl24_w[i], exp_bounded(arg), acc);            // arg in [-80, 0]: A L <= 40 A / Amin <= 80
     }
     total += acc;
   }

@@ -91,6 +91,20 @@ def main():
         d = mp.diff(lambda t: mp.legendre(12, t), xi)
         mp_w.append(2 / ((1 - xi ** 2) * d ** 2))
     assert abs(sum(mp_w) - 2) < mp.mpf(10) ** -30
+
+    def gauss_legendre(nq):
+        xs, ws = [], []
+        x0, _ = np.polynomial.legendre.leggauss(nq)
+        for i in range(nq):
+            xi = mp.mpf(float(x0[i]))
+            for _ in range(4):
+                xi = xi - mp.legendre(nq, xi) / mp.diff(lambda t: mp.legendre(nq, t), xi)
+            d = mp.diff(lambda t: mp.legendre(nq, t), xi)
+            xs.append(xi)
+            ws.append(2 / ((1 - xi ** 2) * d ** 2))
+        assert abs(sum(ws) - 2) < mp.mpf(10) ** -30
+        return xs, ws
+    gl24_x, gl24_w = gauss_legendre(24)
     # e^r on |r| <= ln2/2 (+1%): degree-11 Chebyshev interpolant, monomial basis
     rmax = mp.log(2) / 2 * mp.mpf("1.01")
     pe = cheb_monomial(lambda r: mp.exp(r), -rmax, rmax, 11)
@@ -145,6 +159,8 @@ def main():
             mp.nstr(1 / ln2, 20), mp.nstr(ln2_hi, 20), mp.nstr(ln2_lo, 20)))
         f.write("#define SPART_GL12_X {" + ", ".join(mp.nstr(v, 20) for v in mp_x) + "}\n")
         f.write("#define SPART_GL12_W {" + ", ".join(mp.nstr(v, 20) for v in mp_w) + "}\n")
+        f.write("#define SPART_GL24_X {" + ", ".join(mp.nstr(v, 20) for v in gl24_x) + "}\n")
+        f.write("#define SPART_GL24_W {" + ", ".join(mp.nstr(v, 20) for v in gl24_w) + "}\n")
     print("wrote", OUT)
 
 
