@@ -245,7 +245,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
     int next = 0;
     int ang = 0, smp = kLidfSpw;   // no task yet
     double g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0;
-    double u = 0.0, uf = 0.0, unf = 0.0, k0 = 0.0, theta2 = 0.0;
+    double u = 0.0, uf = 0.0, k0 = 0.0, theta2 = 0.0;
     double num = 0.0;              // 2 y + theta2 of a task that converged in stage A
     bool direct = false;
     bool running = false;
@@ -264,7 +264,6 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
         un = fma(un, u, g0);
         if (!(fabs(un - u) > 1e-8)) {
           uf = u;
-          unf = un;
           running = false;
         }
         u = un;
@@ -281,12 +280,13 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
         un = fma(un, u, g2);
         un = fma(un, u, g1);
         un = fma(un, u, g0);
-        const bool stop = !(fabs(un - u) > 1e-8);
-        const bool fin = running && stop;
-        uf = fin ? u : uf;
-        unf = fin ? un : unf;
-        u = running ? un : u;
-        running = running && !stop;
+        // first step with |du| <= 1e-8: remember the iterate it started from; u itself may keep
+        // iterating (a finished lane is never looked at again), which saves the selects on u
+        if (running && !(fabs(un - u) > 1e-8)) {
+          uf = u;
+          running = false;
+        }
+        u = un;
       }
 #endif
       const unsigned idle = __ballot_sync(full, !running);
@@ -294,10 +294,18 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
       if (next < kLidfTasks) {
         if (nidle >= SPART_LIDF_BATCH_B || next == 0) {
           if (!running) {
-            // y~(u) = 2 u_new - u - k0, so 2 y + theta2 = 4 u_new - 2 u - 2 k0 + theta2
-            if (smp < nvalid)
+            // y~(u) = 2 g(u) - u - k0, so 2 y + theta2 = 4 g(u) - 2 u - 2 k0 + theta2 at the last iterate
+            if (smp < nvalid) {
+              double unf = fma(g7, uf, g6);
+              unf = fma(unf, uf, g5);
+              unf = fma(unf, uf, g4);
+              unf = fma(unf, uf, g3);
+              unf = fma(unf, uf, g2);
+              unf = fma(unf, uf, g1);
+              unf = fma(unf, uf, g0);
               out[ang * stride_ang + smp * stride_smp] =
                   (direct ? num : 2.0 * (2.0 * unf - uf - k0) + theta2) * (1.0 / SPART_PI);
+            }
             const int task = next + __popc(idle & lt_mask);
             if (task < kLidfTasks) {
               ang = task / kLidfSpw;
@@ -336,9 +344,17 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
       }
       if (++iters > (1 << 22)) break;
     }
-    if (smp < nvalid)
+    if (smp < nvalid) {
+      double unf = fma(g7, uf, g6);
+      unf = fma(unf, uf, g5);
+      unf = fma(unf, uf, g4);
+      unf = fma(unf, uf, g3);
+      unf = fma(unf, uf, g2);
+      unf = fma(unf, uf, g1);
+      unf = fma(unf, uf, g0);
       out[ang * stride_ang + smp * stride_smp] =
           (direct ? num : 2.0 * (2.0 * unf - uf - k0) + theta2) * (1.0 / SPART_PI);
+    }
   }
 }
 
