@@ -138,10 +138,12 @@ constexpr int kLidfSpw = SPART_LIDF_SPW;
 // The iterates are reproduced in two stages:
 //   A  exact steps (one sincos each) until the remaining distance to the fixed point is below
 //      ~SPART_LIDF_TAU: |dx| <= TAU (1 - y'(x))/2;
-//   B  from that iterate x_s on, y is replaced by its degree-7 Taylor polynomial around x_s.
-//      |x - x_s| <= ~TAU = 1.6e-2 for all later iterates, so the truncation error is below
-//      65/8! * TAU^8 = 7e-18 and the map u <- g(u) = (u + y~(u) + theta2 - x_s)/2 is one
-//      Horner evaluation (7 FMA) per step instead of a sincos.  Stage B continues the SAME
+//   B  from that iterate x_s on, y is replaced by its degree-SPART_LIDF_DEG Taylor polynomial
+//      around x_s.  |x - x_s| <= ~TAU for all later iterates, so the truncation error is below
+//      (|a| + 2^DEG |b|) TAU^(DEG+1) / (DEG+1)! (3e-15 for DEG = 6, TAU = 1.6e-2; measured 5e-15 on
+//      F) and the map
+//      u <- g(u) = (u + y~(u) + theta2 - x_s)/2 is one Horner evaluation per step instead of a
+//      sincos.  Stage B continues the SAME
 //      sequence with the same stopping rule; against the step-by-step iteration the final
 //      F values agree to 1e-15 over the whole |a| + |b| <= 1 domain (tools/check_lidf_taylor.py).
 // Both stages run as a warp-wide task queue over the 12 * kLidfSpw (sample, angle) pairs: a
@@ -150,7 +152,42 @@ constexpr int kLidfSpw = SPART_LIDF_SPW;
 // code on almost every step).  sA/sB: the warp's LIDFa/LIDFb; sX: per-task hand-over value
 // (x_s, or 2 y + theta2 for a task that already converged in stage A, flagged in sDone).
 // Results F(theta) go to global memory at out[ang * stride_ang + smp * stride_smp].
-#define SPART_LIDF_TAU 1.6e-2
+#ifndef SPART_LIDF_DEG
+#define SPART_LIDF_DEG 6         // degree of the Taylor model of y around the hand-over iterate
+#endif
+#ifndef SPART_LIDF_TAU
+#define SPART_LIDF_TAU 1.6e-2    // hand-over distance; truncation error ~ 2^DEG TAU^(DEG+1) / (DEG+1)!
+#endif
+constexpr int kLidfDeg = SPART_LIDF_DEG;
+
+// u <- g(u): Horner evaluation of the degree-kLidfDeg polynomial map of stage B
+__device__ __forceinline__ double lidf_poly(const double (&g)[kLidfDeg + 1], double u) {
+  double r = g[kLidfDeg];
+#pragma unroll
+  for (int k = kLidfDeg - 1; k >= 0; --k) r = fma(r, u, g[k]);
+  return r;
+}
+
+// coefficients of g(u) = (u + y~(u) + k0) / 2, y~ = sum_k y^(k)(xs) u^k / k!, from sin/cos of xs:
+// y^(k) = a sin^(k) x + b 2^(k-1) sin^(k) 2x and sin^(k) cycles through (s, c, -s, -c)
+__device__ __forceinline__ void lidf_poly_setup(double a, double b, double s, double c, double k0,
+                                                double (&g)[kLidfDeg + 1]) {
+  const double s2 = 2.0 * s * c, c2 = fma(2.0 * c, c, -1.0);
+  double fact = 1.0, pow2 = 0.5;        // k!, 2^(k-1)
+#pragma unroll
+  for (int k = 0; k <= kLidfDeg; ++k) {
+    if (k > 0) {
+      fact *= (double)k;
+      pow2 *= 2.0;
+    }
+    const double t1 = (k & 1) ? c : s, t2 = (k & 1) ? c2 : s2;
+    const double sign = (k & 2) ? -1.0 : 1.0;
+    g[k] = (sign * 0.5 / fact) * fma(a, t1, (b * pow2) * t2);
+  }
+  g[0] += 0.5 * k0;
+  g[1] += 0.5;
+}
+
 #ifndef SPART_LIDF_ASTEPS
 #define SPART_LIDF_ASTEPS 2      // exact steps per bookkeeping round
 #endif
@@ -244,7 +281,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
   {
     int next = 0;
     int ang = 0, smp = kLidfSpw;   // no task yet
-    double g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0;
+    double g[kLidfDeg + 1] = {0.0};
     double u = 0.0, uf = 0.0, k0 = 0.0, theta2 = 0.0;
     double num = 0.0;              // 2 y + theta2 of a task that converged in stage A
     bool direct = false;
@@ -255,13 +292,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
       // up to SPART_LIDF_BSTEPS polynomial steps per bookkeeping round; converged lanes drop out of
       // the loop (hardware divergence), so a step costs the 7 FMA, the difference and the test only
       for (int rep = 0; rep < SPART_LIDF_BSTEPS && running; ++rep) {
-        double un = fma(g7, u, g6);
-        un = fma(un, u, g5);
-        un = fma(un, u, g4);
-        un = fma(un, u, g3);
-        un = fma(un, u, g2);
-        un = fma(un, u, g1);
-        un = fma(un, u, g0);
+        const double un = lidf_poly(g, u);
         if (!(fabs(un - u) > 1e-8)) {
           uf = u;
           running = false;
@@ -273,13 +304,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
       // converges inside the round freezes (u, u_new) of its last step with selects
 #pragma unroll
       for (int rep = 0; rep < SPART_LIDF_BSTEPS; ++rep) {
-        double un = fma(g7, u, g6);
-        un = fma(un, u, g5);
-        un = fma(un, u, g4);
-        un = fma(un, u, g3);
-        un = fma(un, u, g2);
-        un = fma(un, u, g1);
-        un = fma(un, u, g0);
+        const double un = lidf_poly(g, u);
         // first step with |du| <= 1e-8: remember the iterate it started from; u itself may keep
         // iterating (a finished lane is never looked at again), which saves the selects on u
         if (running && !(fabs(un - u) > 1e-8)) {
@@ -296,13 +321,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
           if (!running) {
             // y~(u) = 2 g(u) - u - k0, so 2 y + theta2 = 4 g(u) - 2 u - 2 k0 + theta2 at the last iterate
             if (smp < nvalid) {
-              double unf = fma(g7, uf, g6);
-              unf = fma(unf, uf, g5);
-              unf = fma(unf, uf, g4);
-              unf = fma(unf, uf, g3);
-              unf = fma(unf, uf, g2);
-              unf = fma(unf, uf, g1);
-              unf = fma(unf, uf, g0);
+              const double unf = lidf_poly(g, uf);
               out[ang * stride_ang + smp * stride_smp] =
                   (direct ? num : 2.0 * (2.0 * unf - uf - k0) + theta2) * (1.0 / SPART_PI);
             }
@@ -319,17 +338,8 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
                 const double a = sA[smp], b = sB[smp];
                 double s, c;
                 sincos_small(xs, s, c);
-                const double s2 = 2.0 * s * c, c2 = fma(2.0 * c, c, -1.0);
                 k0 = theta2 - xs;
-                // g(u) = (u + y~(u) + k0) / 2 with y~ = sum_k y^(k)(xs) u^k / k!
-                g0 = 0.5 * (fma(a, s, 0.5 * b * s2) + k0);
-                g1 = 0.5 * (1.0 + fma(a, c, b * c2));
-                g2 = -(0.5 / 2.0) * fma(a, s, 2.0 * b * s2);
-                g3 = -(0.5 / 6.0) * fma(a, c, 4.0 * b * c2);
-                g4 = (0.5 / 24.0) * fma(a, s, 8.0 * b * s2);
-                g5 = (0.5 / 120.0) * fma(a, c, 16.0 * b * c2);
-                g6 = -(0.5 / 720.0) * fma(a, s, 32.0 * b * s2);
-                g7 = -(0.5 / 5040.0) * fma(a, c, 64.0 * b * c2);
+                lidf_poly_setup(a, b, s, c, k0, g);
                 u = 0.0;
                 running = true;
               }
@@ -345,13 +355,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
       if (++iters > (1 << 22)) break;
     }
     if (smp < nvalid) {
-      double unf = fma(g7, uf, g6);
-      unf = fma(unf, uf, g5);
-      unf = fma(unf, uf, g4);
-      unf = fma(unf, uf, g3);
-      unf = fma(unf, uf, g2);
-      unf = fma(unf, uf, g1);
-      unf = fma(unf, uf, g0);
+      const double unf = lidf_poly(g, uf);
       out[ang * stride_ang + smp * stride_smp] =
           (direct ? num : 2.0 * (2.0 * unf - uf - k0) + theta2) * (1.0 / SPART_PI);
     }
