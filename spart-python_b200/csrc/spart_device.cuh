@@ -85,6 +85,10 @@ __constant__ double c_tau_invhalf[SPART_TAU_NINT];
 #define SPART_NQ 12
 __constant__ double c_gl_x[SPART_NQ] = SPART_GL12_X;
 __constant__ double c_gl_w[SPART_NQ] = SPART_GL12_W;
+// 6-point rule for the narrow last layer of the hot-spot integral
+#define SPART_NQ1 6
+__constant__ double c_gl6_x[SPART_NQ1] = SPART_GL6_X;
+__constant__ double c_gl6_w[SPART_NQ1] = SPART_GL6_W;
 // 24-point rule for the two wide panels of the hot-spot integral
 #define SPART_NQ2 24
 __constant__ double c_gl24_x[SPART_NQ2] = SPART_GL24_X;
@@ -571,7 +575,7 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
 //     integrand is analytic; on a panel its exponent varies by at most ~40 and the high-order
 //     rule resolves it to ~4e-15 (tools/check notes in DESIGN.md: 2 x 24 nodes are as accurate
 //     as 10 x 12 or the reference's 60 x 21).
-// All lanes run the same trip counts (no divergence); cost 96 + 25 exp instead of 557.
+// All lanes run the same trip counts (no divergence); cost 96 + 12 exp instead of 557.
 #define SPART_NP 2
 __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI, double q, double dso,
                                                   double& sumpso_ilai, double& pso2w) {
@@ -612,13 +616,12 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
   // Pso[60]: mean over [-1 - 1/60, -1] (sailh.py:219)
   const double dx = 1.0 / 60.0;
   const double xc = -1.0 - 0.5 * dx;
-  const double ec = exp_fast(alpha * xc);
   double acc = 0.0;
 #pragma unroll
-  for (int i = 0; i < SPART_NQ; ++i) {
-    const double x = fma(0.5 * dx, c_gl_x[i], xc);
-    const double arg = fma(A, x, Cq * (1.0 - ec * exp_fast((0.5 * dx * alpha) * c_gl_x[i])));
-    acc = fma(c_gl_w[i], exp_fast(arg), acc);
+  for (int i = 0; i < SPART_NQ1; ++i) {      // the layer is 1/60 wide: a 6-point rule resolves it to 1e-14
+    const double x = fma(0.5 * dx, c_gl6_x[i], xc);
+    const double arg = fma(A, x, Cq * (1.0 - exp_fast(alpha * x)));
+    acc = fma(c_gl6_w[i], exp_fast(arg), acc);
   }
   pso2w = 0.5 * acc;
 }

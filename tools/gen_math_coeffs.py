@@ -105,6 +105,7 @@ def main():
         assert abs(sum(ws) - 2) < mp.mpf(10) ** -30
         return xs, ws
     gl24_x, gl24_w = gauss_legendre(24)
+    gl6_x, gl6_w = gauss_legendre(6)
     # e^r on |r| <= ln2/2 (+1%): degree-11 Chebyshev interpolant, monomial basis
     rmax = mp.log(2) / 2 * mp.mpf("1.01")
     pe = cheb_monomial(lambda r: mp.exp(r), -rmax, rmax, 11)
@@ -159,6 +160,8 @@ def main():
             mp.nstr(1 / ln2, 20), mp.nstr(ln2_hi, 20), mp.nstr(ln2_lo, 20)))
         f.write("#define SPART_GL12_X {" + ", ".join(mp.nstr(v, 20) for v in mp_x) + "}\n")
         f.write("#define SPART_GL12_W {" + ", ".join(mp.nstr(v, 20) for v in mp_w) + "}\n")
+        f.write("#define SPART_GL6_X {" + ", ".join(mp.nstr(v, 20) for v in gl6_x) + "}\n")
+        f.write("#define SPART_GL6_W {" + ", ".join(mp.nstr(v, 20) for v in gl6_w) + "}\n")
         f.write("#define SPART_GL24_X {" + ", ".join(mp.nstr(v, 20) for v in gl24_x) + "}\n")
         f.write("#define SPART_GL24_W {" + ", ".join(mp.nstr(v, 20) for v in gl24_w) + "}\n")
     print("wrote", OUT)
