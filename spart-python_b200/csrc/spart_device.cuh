@@ -251,6 +251,18 @@ __device__ __forceinline__ double exp_clamp(double x) {
   return p * __hiloint2double((k + 1023) << 20, 0);
 }
 
+// exp_clamp for arguments that are never large and positive (-tau/mu, -m LAI, ...): only the lower
+// clamp is needed.
+__device__ __forceinline__ double exp_neg(double x) {
+#if !SPART_FAST_EXP
+  return exp(x);
+#endif
+  const double xc = (x < -700.0) ? -700.0 : x;
+  int k;
+  const double p = exp_core(xc, k);
+  return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
 // exp for call sites that guarantee |x| <= 700 for finite inputs (NaN still propagates).
 __device__ __forceinline__ double exp_bounded(double x) {
 #if !SPART_FAST_EXP
@@ -411,7 +423,7 @@ __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* l
     const double b = (1.0 - rq + tq + D) * rcp_fast(2.0 * t);
     // b ** (N - 1): b >= 1 and |(N-1) ln b| is O(1), so exp_fast(y ln b) is accurate to a few ulp;
     // the exact cases of pow are kept (y == 0 -> 1, b == inf -> inf).
-    const double bNm1 = (Nm1 == 0.0) ? 1.0 : exp_fast(Nm1 * log_fast(b));
+    const double bNm1 = (Nm1 == 0.0) ? 1.0 : exp_clamp(Nm1 * log_fast(b));
     const double bN2 = bNm1 * bNm1;
     const double a2 = a * a;
     const double inv_d2 = rcp_fast(a2 * bN2 - 1.0);
@@ -434,7 +446,7 @@ __device__ __forceinline__ void bsm_point(const SoilPar& S, const double* lc, do
   if (S.mu > 0.0) {
     const double rbac = 1.0 - (1.0 - rdry) * (rdry * lc[LC_SOILC1] + 1.0 - rdry);
     const double p = lc[LC_SOILP], Rw = lc[LC_SOILRW];
-    const double tw1 = exp_clamp(-2.0 * lc[LC_KW] * S.film);
+    const double tw1 = exp_neg(-2.0 * lc[LC_KW] * S.film);
     double fk = S.emu;           // Poisson weight k = 0
     double acc = rdry * fk;
     double tw = 1.0;
@@ -482,7 +494,7 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
   const double rinf = (a - m) * rcp_fast(sigb);
   const double rinf2 = rinf * rinf;
 
-  const double e1 = exp_clamp(-m * LAI);
+  const double e1 = exp_neg(-m * LAI);
   const double e2 = e1 * e1;
   const double tau_ss = G.tau_ss, tau_oo = G.tau_oo;
   const double inv_km = rcp_fast(k + m), inv_Km = rcp_fast(K + m);
@@ -685,7 +697,7 @@ __device__ __forceinline__ AtmOptics smac_band(const AtmSample& S, const double*
   const double ss = us * inv_q;
   const double q1 = 2.0 + 3.0 * us + h3 * us * (1.0 + 2.0 * us);
   const double q2 = 2.0 - 3.0 * us - h3 * us * (1.0 - 2.0 * us);
-  const double Eu = exp_clamp(-taup * inv_us), Ev = exp_clamp(-taup * inv_uv);
+  const double Eu = exp_neg(-taup * inv_us), Ev = exp_neg(-taup * inv_uv);
   const double q3 = q2 * Eu;
   const double wsd = c[SM_WW] * ss * inv_delta;
   const double c1 = wsd * (q1 * eak * opb + q3 * omb);
@@ -711,8 +723,8 @@ __device__ __forceinline__ AtmOptics smac_band(const AtmSample& S, const double*
   const double Res_6s = (c[SM_REST1] + c[SM_REST2] * tt + c[SM_REST3] * (tt * tt)) + c[SM_REST4] * (tt * tt * tt);
   const double atm_ref = ray_ref - Res_ray + aer_ref - Res_aer + Res_6s;
 
-  const double ta_ss = exp_clamp(-tautot * inv_us);
-  const double ta_oo = exp_clamp(-tautot * inv_uv);
+  const double ta_ss = exp_neg(-tautot * inv_us);
+  const double ta_oo = exp_neg(-tautot * inv_uv);
   AtmOptics O;
   O.Ta_s = ttetas;
   O.Ta_o = ttetav;
