@@ -130,6 +130,48 @@ __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
   cs = __hiloint2double(__double2hiint(ca) ^ (((q + 1) & 2) << 30), __double2loint(ca));
 }
 
+// ---- polynomial evaluation -------------------------------------------------------------------
+// poly_eval<DEG, WAYS>: WAYS = 1 is a single Horner chain; WAYS = 2 / 4 evaluate the coefficients
+// of equal index mod WAYS as independent Horner chains in x^WAYS (a few extra operations, 1/WAYS
+// of the dependency depth) -- the band kernel runs 3 warps per scheduler and is bound by the
+// latency of dependent DFMAs, not by their count.
+#ifndef SPART_TAU_SPLIT
+#define SPART_TAU_SPLIT 2
+#endif
+#ifndef SPART_EXP_SPLIT
+#define SPART_EXP_SPLIT 2
+#endif
+#ifndef SPART_LOG_SPLIT
+#define SPART_LOG_SPLIT 2
+#endif
+template <int DEG, int WAYS>
+__device__ __forceinline__ double poly_eval(const double* c, double x) {
+  if constexpr (WAYS == 1) {
+    double p = c[DEG];
+#pragma unroll
+    for (int i = DEG - 1; i >= 0; --i) p = fma(p, x, c[i]);
+    return p;
+  } else {
+    double xw = x * x;
+    if constexpr (WAYS == 4) xw = xw * xw;
+    double q[WAYS];
+#pragma unroll
+    for (int w = 0; w < WAYS; ++w) {
+      const int top = DEG - ((DEG - w) % WAYS);   // largest index <= DEG congruent to w
+      double p = c[top];
+#pragma unroll
+      for (int i = top - WAYS; i >= 0; i -= WAYS) p = fma(p, xw, c[i]);
+      q[w] = p;
+    }
+    if constexpr (WAYS == 2) {
+      return fma(q[1], x, q[0]);
+    } else {
+      const double x2 = x * x;
+      return fma(fma(q[3], x, q[2]), x2, fma(q[1], x, q[0]));
+    }
+  }
+}
+
 // ---- reciprocal without the slow path ---------------------------------------------------------
 // `1.0 / x` compiles to MUFU.RCP64H + 5 DFMA + a range check that branches to an out-of-line
 // fix-up for subnormal / huge operands (~12 instructions and two basic-block boundaries per
@@ -210,10 +252,7 @@ __device__ __forceinline__ double exp_core(double x, int& k) {
   const double r8 = r4 * r4;
   return fma(b2, r8, fma(b1, r4, b0));
 #else
-  double p = c_exp_poly[11];
-#pragma unroll
-  for (int i = 10; i >= 0; --i) p = fma(p, r, c_exp_poly[i]);
-  return p;
+  return poly_eval<11, SPART_EXP_SPLIT>(c_exp_poly, r);
 #endif
 }
 
@@ -287,9 +326,7 @@ __device__ __forceinline__ double log_fast(double x) {
   const double m = __hiloint2double(mh, __double2loint(x));
   const double s = (m - 1.0) * rcp_fast(m + 1.0);
   const double z = s * s;
-  double p = c_log_poly[8];
-#pragma unroll
-  for (int i = 7; i >= 0; --i) p = fma(p, z, c_log_poly[i]);
+  const double p = poly_eval<8, SPART_LOG_SPLIT>(c_log_poly, z);
   const double s2 = s + s;
   const double l = fma(s2 * z, p, s2);     // 2 atanh(s) = ln m
   // int -> double without I2F: 2^52 + 2^31 + e, minus the bias
@@ -351,9 +388,7 @@ __device__ __forceinline__ double plate_tau(double K, const TauTable* tab) {
   const double d0 = fma(b1, u4, b0), d1 = fma(b3, u4, b2);
   const double p = fma(c[16], u8 * u8, fma(d1, u8, d0));
 #else
-  double p = c[SPART_TAU_DEG];
-#pragma unroll
-  for (int i = SPART_TAU_DEG - 1; i >= 0; --i) p = fma(p, u, c[i]);
+  const double p = poly_eval<SPART_TAU_DEG, SPART_TAU_SPLIT>(c, u);
 #endif
   if (K < 1.0) {
     const double e1 = fma(K, p, -0.57721566490153286061 - log_fast(K));
