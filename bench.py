@@ -65,7 +65,7 @@ def kernel_source_sha():
         for line in txt.splitlines():
             m = re.search(r"Function : (\S+)", line)
             if m:
-                keep = bool(re.search(r"lidf_kernel|geometry_kernelPK|band_kernelPK", m.group(1)))
+                keep = bool(re.search(r"lidf_kernel|geometry_kernelPK|band_kernelILb1EEvPK", m.group(1)))
             if keep:
                 h.update(re.sub(r"/\*[0-9a-f]{16}\*/", "", line).encode())     # drop the encoding column
         return "sass:" + h.hexdigest()[:16]

@@ -789,4 +789,131 @@ __device__ __forceinline__ void smac_toa_band(const AtmSample& S, const double* 
   L_TOA = (conv_ea * etscale) * R_TOA;
 }
 
+// ---- SMAC with block-uniform geometry (SPART_FLAG_UNIFORM_GEOMETRY) -------------------------
+// When every sample shares the sun / observer angles, all sub-expressions of smac_band() that
+// depend only on the geometry and the band coefficients are formed once per block and band
+// (smac_fold_geometry, one thread per band) and kept in shared memory; the per-sample work keeps
+// only what depends on pressure, aerosol load and the gas columns.  The sums are re-associated
+// with respect to smac_band() (a few ulp), which is why this is a separate code path.
+enum UgIndex {
+  UG_TS0 = 0, UG_TS1, UG_TS2,       // ttetas = TS0 + TS1 taup550 + TS2 Peq
+  UG_TV0, UG_TV1, UG_TV2,           // ttetav
+  UG_RAYREF,                        // ray_ref / Peq
+  UG_RESRAY,                        // Res_ray
+  UG_Q1OPB, UG_Q2OMB, UG_Q1OMB, UG_Q2OPB,
+  UG_X1W, UG_Y2W, UG_Z3,            // weights of the three aerosol reflectance terms
+  UG_MCKSI, UG_INVUS, UG_INVUV,
+  UG_GO2, UG_GCO2, UG_GCH4, UG_GNO2, UG_GCO,   // n ln m of the uniformly mixed gases
+  UG_COUNT
+};
+
+struct AtmGeometry {   // the geometry-only members of AtmSample
+  double us, uv, m, lm, cksi, ksiD, ray_phase, inv_us, inv_uv, inv_1pus, inv_1puv, aa3;
+};
+
+__device__ __forceinline__ void smac_fold_geometry(const AtmGeometry& S, const double* c, double* u) {
+  const double us = S.us, uv = S.uv, inv_us = S.inv_us, inv_uv = S.inv_uv;
+  u[UG_TS0] = c[SM_A0T] + c[SM_A3T] * S.inv_1pus;
+  u[UG_TS1] = c[SM_A1T] * inv_us;
+  u[UG_TS2] = c[SM_A2T] * S.inv_1pus;
+  u[UG_TV0] = c[SM_A0T] + c[SM_A3T] * S.inv_1puv;
+  u[UG_TV1] = c[SM_A1T] * inv_uv;
+  u[UG_TV2] = c[SM_A2T] * S.inv_1puv;
+  const double taur = c[SM_TAUR];
+  const double inv_usuv = inv_us * inv_uv;
+  const double rr = taur * S.ray_phase * inv_usuv;
+  u[UG_RAYREF] = 0.25 * rr;
+  u[UG_RESRAY] = c[SM_RESR1] + c[SM_RESR2TAUR] * S.ray_phase * inv_usuv + c[SM_RESR3] * (rr * rr);
+  const double ksiD = S.ksiD, ksi2 = ksiD * ksiD;
+  const double aer_phase = c[SM_A0P] + c[SM_A1P] * ksiD + c[SM_A2P] * ksi2 + c[SM_A3P] * (ksi2 * ksiD) +
+                           c[SM_A4P] * (ksi2 * ksi2);
+  const double wo = c[SM_WO], ak2 = c[SM_AK2], ak = c[SM_AK];
+  const double opb = c[SM_OPB], omb = c[SM_OMB], g3 = c[SM_G3], h3 = c[SM_H3], akd3 = c[SM_AKD3];
+  const double us2 = us * us;
+  const double inv_q = 1.0 / (1.0 - ak2 * us2);
+  const double e = -0.75 * us2 * wo * inv_q;
+  const double f = -0.25 * h3 * us2 * wo * inv_q;
+  const double dp = e * inv_us * (1.0 / 3.0) + us * f;
+  const double d = e + f;
+  const double q1 = 2.0 + 3.0 * us + h3 * us * (1.0 + 2.0 * us);
+  const double q2 = 2.0 - 3.0 * us - h3 * us * (1.0 - 2.0 * us);
+  u[UG_Q1OPB] = q1 * opb;
+  u[UG_Q2OMB] = q2 * omb;
+  u[UG_Q1OMB] = q1 * omb;
+  u[UG_Q2OPB] = q2 * opb;
+  const double wss = c[SM_WW] * us * inv_q;
+  const double g3uv = g3 * uv;
+  const double z = d - g3uv * dp + wo * aer_phase * 0.25;
+  const double aa1 = uv / (1.0 + ak * uv);
+  const double aa2 = uv / (1.0 - ak * uv);
+  u[UG_X1W] = wss * (1.0 - g3uv * akd3) * aa1 * inv_usuv;
+  u[UG_Y2W] = wss * (1.0 + g3uv * akd3) * aa2 * inv_usuv;
+  u[UG_Z3] = z * S.aa3 * inv_usuv;
+  u[UG_MCKSI] = S.m * S.cksi;
+  u[UG_INVUS] = inv_us;
+  u[UG_INVUV] = inv_uv;
+  u[UG_GO2] = c[SM_NO2] * S.lm;
+  u[UG_GCO2] = c[SM_NCO2] * S.lm;
+  u[UG_GCH4] = c[SM_NCH4] * S.lm;
+  u[UG_GNO2] = c[SM_NNO2] * S.lm;
+  u[UG_GCO] = c[SM_NCO] * S.lm;
+}
+
+struct AtmColumn {   // the per-sample members of AtmSample
+  double Peq, lo3, lh2o, lpeq, taup550;
+};
+
+__device__ __forceinline__ void smac_toa_band_uniform(const AtmColumn& S, const double* c, const double* u,
+                                                      double conv_ea, double etscale, double rv_so, double rv_do,
+                                                      double rv_dd, double rv_sd, double& R_TOC, double& R_TOA,
+                                                      double& L_TOA) {
+  const double Peq = S.Peq, taup550 = S.taup550;
+  const double taup = c[SM_A0TAUP] + c[SM_A1TAUP] * taup550;
+
+  double gsum = 0.0;
+  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp_clamp(c[SM_NO3] * S.lo3);
+  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp_clamp(c[SM_NH2O] * S.lh2o);
+  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp_clamp(fma(c[SM_NPO2], S.lpeq, u[UG_GO2]));
+  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp_clamp(fma(c[SM_NPCO2], S.lpeq, u[UG_GCO2]));
+  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp_clamp(fma(c[SM_NPCH4], S.lpeq, u[UG_GCH4]));
+  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp_clamp(fma(c[SM_NPNO2], S.lpeq, u[UG_GNO2]));
+  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp_clamp(fma(c[SM_NPCO], S.lpeq, u[UG_GCO]));
+  const double tg = exp_clamp(gsum);
+
+  const double ra_dd = c[SM_A0S] * Peq + c[SM_A3S] + c[SM_A1S] * taup550 + c[SM_A2S] * taup550 * taup550;
+  const double ttetas = fma(u[UG_TS2], Peq, fma(u[UG_TS1], taup550, u[UG_TS0]));
+  const double ttetav = fma(u[UG_TV2], Peq, fma(u[UG_TV1], taup550, u[UG_TV0]));
+
+  const double eak = exp_clamp(c[SM_AK] * taup);
+  const double emak = rcp_fast(eak);
+  const double inv_delta = rcp_fast(eak * c[SM_OPB2] - emak * c[SM_OMB2]);
+  const double Eu = exp_neg(-taup * u[UG_INVUS]), Ev = exp_neg(-taup * u[UG_INVUV]);
+  const double c1 = fma(u[UG_Q1OPB], eak, u[UG_Q2OMB] * Eu);
+  const double c2 = fma(u[UG_Q1OMB], emak, u[UG_Q2OPB] * Eu);
+  const double t1 = u[UG_X1W] * c1 * (1.0 - Ev * emak);
+  const double t2 = u[UG_Y2W] * c2 * (1.0 - Ev * eak);
+  const double aer_ref = fma(inv_delta, t1 - t2, u[UG_Z3] * (1.0 - Ev * Eu));
+
+  const double mcksi = u[UG_MCKSI];
+  const double ta = taup * mcksi;
+  const double Res_aer = (c[SM_RESA1] + c[SM_RESA2] * ta + c[SM_RESA3] * (ta * ta)) + c[SM_RESA4] * (ta * ta * ta);
+  const double tautot = fma(c[SM_TAUR], Peq, taup);
+  const double tt = tautot * mcksi;
+  const double Res_6s = (c[SM_REST1] + c[SM_REST2] * tt + c[SM_REST3] * (tt * tt)) + c[SM_REST4] * (tt * tt * tt);
+  const double ra_so = u[UG_RAYREF] * Peq - u[UG_RESRAY] + aer_ref - Res_aer + Res_6s;
+
+  const double ta_ss = exp_neg(-tautot * u[UG_INVUS]);
+  const double ta_oo = exp_neg(-tautot * u[UG_INVUV]);
+  const double ta_sd = ttetas - ta_ss, ta_do = ttetav - ta_oo;
+
+  // SPART.py:243-252
+  const double inv_ms = rcp_fast(1.0 - rv_dd * ra_dd);
+  const double rtoa0 = ra_so + ta_ss * rv_so * ta_oo;
+  const double rtoa1 = (ta_sd * rv_do + ta_ss * rv_sd * ra_dd * rv_do) * ta_oo * inv_ms;
+  const double rtoa2 = (ta_ss * rv_sd + ta_sd * rv_dd) * ta_do * inv_ms;
+  R_TOC = (ta_ss * rv_so + ta_sd * rv_do) * rcp_fast(ta_ss + ta_sd);
+  R_TOA = tg * (rtoa0 + rtoa1 + rtoa2);
+  L_TOA = (conv_ea * etscale) * R_TOA;
+}
+
 }  // namespace spart

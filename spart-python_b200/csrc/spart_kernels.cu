@@ -33,6 +33,9 @@ using namespace spart;
 #ifndef SPART_BAND_CHUNK
 #define SPART_BAND_CHUNK 16
 #endif
+#ifndef SPART_BAND_MINBLOCKS_U
+#define SPART_BAND_MINBLOCKS_U 4
+#endif
 #ifndef SPART_BAND_MINBLOCKS
 #define SPART_BAND_MINBLOCKS 3
 #endif
@@ -583,17 +586,41 @@ constexpr int kBandChunk = SPART_BAND_CHUNK;   // bands handled by one block (pe
 // chunk, blockIdx.y = sample tile.  The per-sample state (leaf, soil, canopy geometry, SMAC
 // scalars: 44 doubles) is read from HBM once per chunk and kept in registers; the per-band
 // constants are warp-uniform shared-memory broadcasts.
-__global__ void __launch_bounds__(kBandThreads, SPART_BAND_MINBLOCKS)
+template <bool kUniform>
+__global__ void __launch_bounds__(kBandThreads, kUniform ? SPART_BAND_MINBLOCKS_U : SPART_BAND_MINBLOCKS)
 band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
             const double* __restrict__ band_table, int nb, double* __restrict__ out) {
   __shared__ TauTable s_tau;
   __shared__ double s_bt[kBandChunk][BT_COUNT];
+  __shared__ double s_ug[kUniform ? kBandChunk : 1][UG_COUNT];
   const int b0 = blockIdx.x * kBandChunk;
   const int nbc = min(kBandChunk, nb - b0);
   load_tau_table(&s_tau);
   for (int i = threadIdx.x; i < nbc * BT_COUNT; i += blockDim.x)
     (&s_bt[0][0])[i] = band_table[(size_t)b0 * BT_COUNT + i];
   __syncthreads();
+  if (kUniform) {
+    // all samples share the geometry: fold it into per-band constants, one thread per band,
+    // from the record of the tile's first sample
+    if (threadIdx.x < nbc) {
+      const int64_t s0 = (int64_t)blockIdx.y * kBandThreads;
+      AtmGeometry g;
+      g.us = rec[R_US * n + s0];
+      g.uv = rec[R_UV * n + s0];
+      g.m = rec[R_M * n + s0];
+      g.lm = rec[R_LM * n + s0];
+      g.cksi = rec[R_CKSI * n + s0];
+      g.ksiD = rec[R_KSID * n + s0];
+      g.ray_phase = rec[R_RAYPH * n + s0];
+      g.inv_us = rec[R_INVUS * n + s0];
+      g.inv_uv = rec[R_INVUV * n + s0];
+      g.inv_1pus = rec[R_INV1PUS * n + s0];
+      g.inv_1puv = rec[R_INV1PUV * n + s0];
+      g.aa3 = rec[R_AA3 * n + s0];
+      smac_fold_geometry(g, &s_bt[threadIdx.x][BT_SMAC], s_ug[threadIdx.x]);
+    }
+    __syncthreads();
+  }
   const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
   if (s >= n) return;
 
@@ -601,23 +628,32 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   const SoilPar S = load_soil(P, ld, rec, n, s);
   const CanopyGeo G = load_geo(P, ld, rec, n, s);
   AtmSample A;
-  A.us = rec[R_US * n + s];
-  A.uv = rec[R_UV * n + s];
-  A.m = rec[R_M * n + s];
-  A.Peq = rec[R_PEQ * n + s];
-  A.lo3 = rec[R_LO3 * n + s];
-  A.lh2o = rec[R_LH2O * n + s];
-  A.lm = rec[R_LM * n + s];
-  A.lpeq = rec[R_LPEQ * n + s];
-  A.cksi = rec[R_CKSI * n + s];
-  A.ksiD = rec[R_KSID * n + s];
-  A.ray_phase = rec[R_RAYPH * n + s];
-  A.taup550 = P[P_AOT * ld + s];
-  A.inv_us = rec[R_INVUS * n + s];
-  A.inv_uv = rec[R_INVUV * n + s];
-  A.inv_1pus = rec[R_INV1PUS * n + s];
-  A.inv_1puv = rec[R_INV1PUV * n + s];
-  A.aa3 = rec[R_AA3 * n + s];
+  AtmColumn C;
+  if (kUniform) {
+    C.Peq = rec[R_PEQ * n + s];
+    C.lo3 = rec[R_LO3 * n + s];
+    C.lh2o = rec[R_LH2O * n + s];
+    C.lpeq = rec[R_LPEQ * n + s];
+    C.taup550 = P[P_AOT * ld + s];
+  } else {
+    A.us = rec[R_US * n + s];
+    A.uv = rec[R_UV * n + s];
+    A.m = rec[R_M * n + s];
+    A.Peq = rec[R_PEQ * n + s];
+    A.lo3 = rec[R_LO3 * n + s];
+    A.lh2o = rec[R_LH2O * n + s];
+    A.lm = rec[R_LM * n + s];
+    A.lpeq = rec[R_LPEQ * n + s];
+    A.cksi = rec[R_CKSI * n + s];
+    A.ksiD = rec[R_KSID * n + s];
+    A.ray_phase = rec[R_RAYPH * n + s];
+    A.taup550 = P[P_AOT * ld + s];
+    A.inv_us = rec[R_INVUS * n + s];
+    A.inv_uv = rec[R_INVUV * n + s];
+    A.inv_1pus = rec[R_INV1PUS * n + s];
+    A.inv_1puv = rec[R_INV1PUV * n + s];
+    A.aa3 = rec[R_AA3 * n + s];
+  }
   const double etscale = rec[R_ETSCALE * n + s];
   double* o = out + ((size_t)s * nb + b0) * SPART_NOUT;
 
@@ -645,7 +681,11 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
       }
     }
     double R_TOC, R_TOA, L_TOA;
-    smac_toa_band(A, &bt[BT_SMAC], bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
+    if (kUniform)
+      smac_toa_band_uniform(C, &bt[BT_SMAC], s_ug[bi], bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA,
+                            L_TOA);
+    else
+      smac_toa_band(A, &bt[BT_SMAC], bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
     o[bi * SPART_NOUT + 0] = R_TOC;
     o[bi * SPART_NOUT + 1] = R_TOA;
     o[bi * SPART_NOUT + 2] = L_TOA;
@@ -1305,7 +1345,10 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
                                                       ctx->d_srf_idx[sensor], ctx->d_srf_len[sensor],
                                                       ctx->d_srf_off[sensor], ctx->d_srf_w[sensor], nb, out_dev);
     } else {
-      band_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+      if (flags & SPART_FLAG_UNIFORM_GEOMETRY)
+        band_kernel<true><<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+      else
+        band_kernel<false><<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
     }
   } else {   // SPART_FP32: the leaf angles are solved inside the geometry kernel
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
