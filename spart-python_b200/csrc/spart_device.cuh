@@ -233,25 +233,46 @@ __constant__ double c_explog_red[4] = {SPART_LOG2E, 6755399441055744.0, SPART_LN
 #define SPART_FAST_LOG 1
 #endif
 
-// e^r * 2^k core shared by both variants: returns the polynomial value p ~ e^r and k.
+// e^x = 2^k * 2^(j/64) * e^r with |r| <= ln2/128: 2^(j/64) comes from a 64-entry shared-memory
+// table (lanes index it independently, which the constant cache would serialise) and e^r - 1 from
+// r + r^2 q(r) with a cubic q: 10 FP64 operations per call instead of 17 for the table-free kernel
+// (degree-11 polynomial), <= 1 ulp (tools/gen_math_coeffs.py).  Every kernel that calls one of the
+// exp_* functions must run exp_table_load() and a __syncthreads() first.
+#ifndef SPART_EXP_TABLE
+#define SPART_EXP_TABLE 1
+#endif
+__constant__ double c_exp2_tab[64] = SPART_EXP2_TABLE;
+__constant__ double c_expt_poly[4] = SPART_EXPT_POLY;
+__constant__ double c_expt_red[4] = {SPART_64_OVER_LN2, 6755399441055744.0, SPART_LN2_64_HI, SPART_LN2_64_LO};
+__shared__ double s_exp2_tab[64];
+
+__device__ __forceinline__ void exp_table_load() {
+#if SPART_EXP_TABLE
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_exp2_tab[i] = c_exp2_tab[i];
+#endif
+}
+
+// core shared by all variants: returns p ~ e^x / 2^k, p in [1, 2), and k.
 __device__ __forceinline__ double exp_core(double x, int& k) {
+#if SPART_EXP_TABLE
+  const double magic = c_expt_red[1];
+  const double t = fma(x, c_expt_red[0], magic);
+  const int nq = __double2loint(t);
+  const double nd = t - magic;
+  double r = fma(-nd, c_expt_red[2], x);
+  r = fma(-nd, c_expt_red[3], r);
+  const double T = s_exp2_tab[nq & 63];
+  k = nq >> 6;
+  const double r2 = r * r;
+  const double q = fma(fma(c_expt_poly[3], r2, c_expt_poly[1]), r, fma(c_expt_poly[2], r2, c_expt_poly[0]));
+  return fma(T, fma(r2, q, r), T);
+#else
   const double magic = c_explog_red[1];
   const double t = fma(x, c_explog_red[0], magic);
   k = __double2loint(t);
   const double kd = t - magic;
   double r = fma(-kd, c_explog_red[2], x);
   r = fma(-kd, c_explog_red[3], r);
-#if SPART_ESTRIN
-  // Estrin's scheme: 15 FP64 operations instead of 11, but a dependency depth of 5 instead of 11
-  const double* c = c_exp_poly;
-  const double r2 = r * r;
-  const double a0 = fma(c[1], r, c[0]), a1 = fma(c[3], r, c[2]), a2 = fma(c[5], r, c[4]);
-  const double a3 = fma(c[7], r, c[6]), a4 = fma(c[9], r, c[8]), a5 = fma(c[11], r, c[10]);
-  const double r4 = r2 * r2;
-  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
-  const double r8 = r4 * r4;
-  return fma(b2, r8, fma(b1, r4, b0));
-#else
   return poly_eval<11, SPART_EXP_SPLIT>(c_exp_poly, r);
 #endif
 }

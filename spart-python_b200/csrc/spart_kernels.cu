@@ -424,6 +424,8 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   const int uniform_geometry = flags & SPART_FLAG_UNIFORM_GEOMETRY;
   const bool soil_spectrum = (flags & SPART_FLAG_SOIL_SPECTRUM) != 0;
   __shared__ double s_cls[13][4];   // ksli, koli, sobli, sofli per leaf-inclination class
+  exp_table_load();
+  __syncthreads();
   const int tid = threadIdx.x;
   const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
   const bool valid = s_raw < n;
@@ -596,6 +598,7 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   const int b0 = blockIdx.x * kBandChunk;
   const int nbc = min(kBandChunk, nb - b0);
   load_tau_table(&s_tau);
+  exp_table_load();
   for (int i = threadIdx.x; i < nbc * BT_COUNT; i += blockDim.x)
     (&s_bt[0][0])[i] = band_table[(size_t)b0 * BT_COUNT + i];
   __syncthreads();
@@ -711,6 +714,7 @@ band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   __shared__ double s_w[kSrfChunk];
   const int b = blockIdx.x;
   load_tau_table(&s_tau);
+  exp_table_load();
   for (int i = threadIdx.x; i < BT_COUNT; i += blockDim.x) s_bt[i] = band_table[(size_t)b * BT_COUNT + i];
   const int64_t s_raw = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
   const bool valid = s_raw < n;
@@ -766,6 +770,7 @@ smac_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   __shared__ double s_c[SM_COUNT];
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < SM_COUNT; i += blockDim.x) s_c[i] = band_table[(size_t)b * BT_COUNT + BT_SMAC + i];
+  exp_table_load();
   __syncthreads();
   const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
   if (s >= n) return;
@@ -796,6 +801,8 @@ __global__ void __launch_bounds__(256)
 sailh_spectra_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
                      const double* __restrict__ rs, const double* __restrict__ rho, const double* __restrict__ tau,
                      int64_t stride, int64_t s0, double* __restrict__ out) {
+  exp_table_load();
+  __syncthreads();
   const int w = blockIdx.x * 256 + threadIdx.x;
   const int64_t s = s0 + blockIdx.y;
   if (w >= SPART_NWL_S || s >= n) return;
@@ -1021,6 +1028,7 @@ spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
                 const double* __restrict__ lc_table, int64_t s0, double* __restrict__ out) {
   __shared__ TauTable s_tau;
   load_tau_table(&s_tau);
+  exp_table_load();
   __syncthreads();
   const int w = blockIdx.x * kSpecThreads + threadIdx.x;
   const int64_t s = s0 + blockIdx.y;

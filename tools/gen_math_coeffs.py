@@ -118,6 +118,40 @@ def main():
         worst_e = max(worst_e, abs(float((mp.mpf(p_) - mp.exp(r)) / mp.exp(r))))
     print("max rel err exp kernel %.2e" % worst_e)
     assert worst_e < 3e-16
+    # table-driven variant: e^x = 2^k * 2^(j/64) * e^r, |r| <= ln2/128; 2^(j/64) from a 64-entry table,
+    # e^r as a degree-5 interpolant
+    rmax_t = mp.log(2) / 128 * mp.mpf("1.01")
+    def QE(r):
+        r = mp.mpf(r)
+        if r == 0:
+            return mp.mpf(1) / 2
+        return (mp.exp(r) - 1 - r) / (r * r)
+    pet = cheb_monomial(QE, -rmax_t, rmax_t, 3)      # e^r = 1 + r + r^2 QE(r)
+    tab = [mp.power(2, mp.mpf(j) / 64) for j in range(64)]
+    ET = [float(v) for v in pet]
+    TAB = [float(v) for v in tab]
+    l64 = mp.log(2) / 64
+    l64_hi = mp.mpf(float(l64))
+    l64_lo = mp.mpf(float(l64 - l64_hi))
+    inv_l64 = float(64 / mp.log(2))
+    worst_t = 0.0
+    rng = np.random.default_rng(0)
+
+    def fma(a, b, c):
+        return float(mp.mpf(a) * mp.mpf(b) + mp.mpf(c))
+    for x_ in np.concatenate([rng.uniform(-700, 700, 3000), rng.uniform(-3, 3, 3000)]):
+        x_ = float(x_)
+        n_ = float(np.rint(x_ * inv_l64))
+        r_ = fma(-n_, float(l64_hi), x_)
+        r_ = fma(-n_, float(l64_lo), r_)
+        r2 = r_ * r_
+        q_ = fma(fma(ET[3], r2, ET[1]), r_, fma(ET[2], r2, ET[0]))
+        t_ = TAB[int(n_) & 63]
+        val = fma(t_, fma(r2, q_, r_), t_)
+        ex = mp.exp(mp.mpf(x_)) / mp.power(2, int(n_) >> 6)
+        worst_t = max(worst_t, abs(float((mp.mpf(val) - ex) / ex)))
+    print("max rel err table exp %.2e" % worst_t)
+    assert worst_t < 2.3e-16
     # log m = 2 s (1 + z PL(z)), s = (m-1)/(m+1), z = s^2, m in [sqrt(1/2), sqrt(2)]
     smax = (mp.sqrt(2) - 1) / (mp.sqrt(2) + 1) * mp.mpf("1.01")
 
@@ -155,6 +189,10 @@ def main():
         f.write("#define SPART_PIO2_HI %s\n#define SPART_PIO2_LO %s\n" % (mp.nstr(hi, 20), mp.nstr(lo, 20)))
         f.write("#define SPART_TWO_OVER_PI %s\n" % mp.nstr(2 / mp.pi, 20))
         f.write("#define SPART_EXP_POLY {" + ", ".join(mp.nstr(v, 20) for v in pe) + "}\n")
+        f.write("#define SPART_EXPT_POLY {" + ", ".join(mp.nstr(v, 20) for v in pet) + "}\n")
+        f.write("#define SPART_EXP2_TABLE {" + ", ".join(mp.nstr(v, 20) for v in tab) + "}\n")
+        f.write("#define SPART_64_OVER_LN2 %s\n#define SPART_LN2_64_HI %s\n#define SPART_LN2_64_LO %s\n" % (
+            mp.nstr(64 / mp.log(2), 20), mp.nstr(l64_hi, 20), mp.nstr(l64_lo, 20)))
         f.write("#define SPART_LOG_POLY {" + ", ".join(mp.nstr(v, 20) for v in pl) + "}\n")
         f.write("#define SPART_LOG2E %s\n#define SPART_LN2_HI %s\n#define SPART_LN2_LO %s\n" % (
             mp.nstr(1 / ln2, 20), mp.nstr(ln2_hi, 20), mp.nstr(ln2_lo, 20)))
