@@ -181,16 +181,25 @@ __device__ __forceinline__ double poly_eval(const double* c, double x) {
 #ifndef SPART_FAST_RCP
 #define SPART_FAST_RCP 1
 #endif
+#ifndef SPART_RCP_ORDER3
+#define SPART_RCP_ORDER3 1
+#endif
 __device__ __forceinline__ double rcp_fast(double x) {
 #if !SPART_FAST_RCP
   return 1.0 / x;
 #else
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#if SPART_RCP_ORDER3
+  // the seed is good to ~2^-20: one third-order step r (1 + e + e^2) leaves e^3 ~ 2^-60
+  const double e = fma(-x, r, 1.0);
+  return fma(r, fma(e, e, e), r);
+#else
   double e = fma(-x, r, 1.0);
   r = fma(r, e, r);
   e = fma(-x, r, 1.0);
   return fma(r, e, r);
+#endif
 #endif
 }
 
@@ -203,12 +212,20 @@ __device__ __forceinline__ double sqrt_fast(double x) {
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
   r = (x == 0.0) ? 0.0 : r;
+#if SPART_RCP_ORDER3
+  // g = x r ~ sqrt(x), e = 1 - x r^2; sqrt(x) = g (1 - e)^(-1/2) = g (1 + e/2 + 3 e^2/8 + O(e^3))
+  const double g = x * r;
+  const double e = fma(-g, r, 1.0);
+  const double t = fma(0.375, e, 0.5) * e;
+  return fma(g, t, g);
+#else
   double g = x * r, h = 0.5 * r;
   double e = fma(-h, g, 0.5);
   g = fma(g, e, g);
   h = fma(h, e, h);
   e = fma(-h, g, 0.5);
   return fma(g, e, g);
+#endif
 #endif
 }
 

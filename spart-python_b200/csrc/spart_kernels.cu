@@ -460,29 +460,50 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     __syncthreads();
   }
   if (!valid) return;
+  // the parameter rows read after the hot-spot integral: start them towards L1 now
+  {
+    const int later[] = {P_LAI, P_Q, P_B, P_LAT, P_LON, P_SMP, P_SMC, P_PA, P_UO3, P_UH2O, P_DOY};
+#pragma unroll
+    for (int i = 0; i < 11; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(P + later[i] * ld + s));
+  }
 
   // 13 leaf-inclination classes, dotted with lidf (sailh.py:81-97)
   double k = 0.0, K = 0.0, bf = 0.0, sob = 0.0, sof = 0.0;
-  double Fprev = 0.0;
+  if (uniform_geometry) {
+    // all twelve F loads are issued before the first use (one memory latency instead of twelve)
+    double F[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) F[i] = rec[(size_t)(kRowF + i) * n + s];
+    double Fprev = 0.0;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      const double Fi = (i < 12) ? F[i < 12 ? i : 0] : 1.0;
+      const double lidf = Fi - Fprev;
+      Fprev = Fi;
+      k += s_cls[i][0] * lidf;
+      K += s_cls[i][1] * lidf;
+      bf += (c_cos_ttli[i] * c_cos_ttli[i]) * lidf;
+      sob += s_cls[i][2] * lidf;
+      sof += s_cls[i][3] * lidf;
+    }
+  } else {
+    double Fprev = 0.0;
+    double Fnext = rec[(size_t)kRowF * n + s];
 #pragma unroll 1
-  for (int i = 0; i < 13; ++i) {
-    const double Fi = (i < 12) ? rec[(size_t)(kRowF + i) * n + s] : 1.0;
-    const double lidf = Fi - Fprev;
-    Fprev = Fi;
-    double ksli, koli, sobli, sofli;
-    if (uniform_geometry) {
-      ksli = s_cls[i][0]; koli = s_cls[i][1]; sobli = s_cls[i][2]; sofli = s_cls[i][3];
-    } else {
+    for (int i = 0; i < 13; ++i) {
+      const double Fi = (i < 12) ? Fnext : 1.0;
+      if (i < 11) Fnext = rec[(size_t)(kRowF + i + 1) * n + s];   // in flight during volscatt_class
+      const double lidf = Fi - Fprev;
+      Fprev = Fi;
       double chi_s, chi_o, frho, ftau;
       volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
                      chi_o, frho, ftau);
-      ksli = chi_s * inv_cs; koli = chi_o * inv_co; sobli = frho * inv_cc; sofli = ftau * inv_cc;
+      k += (chi_s * inv_cs) * lidf;
+      K += (chi_o * inv_co) * lidf;
+      bf += (c_cos_ttli[i] * c_cos_ttli[i]) * lidf;
+      sob += (frho * inv_cc) * lidf;
+      sof += (ftau * inv_cc) * lidf;
     }
-    k += ksli * lidf;
-    K += koli * lidf;
-    bf += (c_cos_ttli[i] * c_cos_ttli[i]) * lidf;
-    sob += sobli * lidf;
-    sof += sofli * lidf;
   }
 
   const double LAI = P[P_LAI * ld + s], q = P[P_Q * ld + s];

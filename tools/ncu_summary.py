@@ -7,6 +7,13 @@ import json
 import sys
 
 
+def base_name(kernel_name):
+    """'void band_kernel<(bool)1>(const double *, ...)' -> 'band_kernel'"""
+    import re
+    m = re.match(r"(?:void\s+)?(?:[A-Za-z_0-9]+::)*([A-Za-z_0-9]+)", kernel_name.strip())
+    return m.group(1) if m else kernel_name
+
+
 def main(path, units=1e6):
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
@@ -22,7 +29,7 @@ def main(path, units=1e6):
 
     out = {}
     for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")].split("(")[0]
+        name = base_name(r[hdr.index("Kernel Name")])
         cyc = g(r, "smsp__cycles_elapsed.avg")
         d = {k: g(r, f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum.per_cycle_elapsed") * cyc
              for k in ("dadd", "dmul", "dfma")}

@@ -49,7 +49,7 @@ def main(tag):
         w.writerow(keep)
         for r in rows[h + 1:]:
             d = dict(zip(hdr, r))
-            d["Kernel Name"] = d["Kernel Name"].split("(")[0]
+            d["Kernel Name"] = ncu_summary.base_name(d["Kernel Name"])
             w.writerow([d[k] for k in keep])
     for name in (f"{tag}_bench.json",):
         line = (go / name).read_text().strip().splitlines()[-1]
@@ -58,7 +58,7 @@ def main(tag):
     dur = {}
     for r in rows[h + 1:]:
         d = dict(zip(hdr, r))
-        k = d["Kernel Name"].split("(")[0]
+        k = ncu_summary.base_name(d["Kernel Name"])
         if k.endswith("_kernel") and "fma_chain" not in k:
             dur.setdefault(k, []).append(float(d["Metric Value"].replace(",", "")))
     tot = sum(sum(v) / len(v) for v in dur.values())
