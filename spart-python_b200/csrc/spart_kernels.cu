@@ -602,7 +602,10 @@ __device__ __forceinline__ SoilPar load_soil(const double* __restrict__ P, int64
   return S;
 }
 
-constexpr int kBandThreads = 128;
+#ifndef SPART_BAND_THREADS
+#define SPART_BAND_THREADS 128
+#endif
+constexpr int kBandThreads = SPART_BAND_THREADS;
 constexpr int kBandChunk = SPART_BAND_CHUNK;   // bands handled by one block (per-sample state is loaded once per chunk)
 
 // One thread per sample, looping over a chunk of up to kBandChunk bands; blockIdx.x = band
