@@ -626,10 +626,11 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   const double As = fmax(Ss, Cs), Ao = fmax(So, Co);
   // true divisions: the quotient is exactly -1 whenever Cs >= Ss (As == Cs), and acos amplifies a
   // 1-ulp deviation from -1 to 1e-8
-  const double bts = acos(-Cs / As), bto = acos(-Co / Ao);
-  double sbto, cbto, sbts, cbts, s2, c2, s1, c1, s3, c3;   // all arguments lie in [0, 2 pi]
-  sincos_small(bto, sbto, cbto);
-  sincos_small(bts, sbts, cbts);
+  const double zs = -Cs / As, zo = -Co / Ao;
+  const double bts = acos(zs), bto = acos(zo);
+  double s2, c2, s1, c1, s3, c3;   // all arguments lie in [0, 2 pi]
+  // sin(acos z) = sqrt(1 - z^2) (>= 0 on [0, pi]); differs from sin of the rounded angle by < 2e-16 absolute
+  const double sbts = sqrt_fast(fma(-zs, zs, 1.0)), sbto = sqrt_fast(fma(-zo, zo, 1.0));
   chi_o = 2.0 / SPART_PI * ((bto - SPART_PI / 2.0) * Co + sbto * So);
   chi_s = 2.0 / SPART_PI * ((bts - SPART_PI / 2.0) * Cs + sbts * Ss);
   const double delta1 = fabs(bts - bto);
