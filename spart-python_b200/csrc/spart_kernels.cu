@@ -424,8 +424,7 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   const int uniform_geometry = flags & SPART_FLAG_UNIFORM_GEOMETRY;
   const bool soil_spectrum = (flags & SPART_FLAG_SOIL_SPECTRUM) != 0;
   __shared__ double s_cls[13][4];   // ksli, koli, sobli, sofli per leaf-inclination class
-  exp_table_load();
-  __syncthreads();
+  exp_table_load();               // published by the barrier below
   const int tid = threadIdx.x;
   const int64_t s_raw = (int64_t)blockIdx.x * kSampleThreads + tid;
   const bool valid = s_raw < n;
@@ -433,6 +432,19 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
 
   // sun / observer geometry (sailh.py:59-78)
   const double tts = P[P_SZA * ld + s], tto = P[P_VZA * ld + s], rel = P[P_RAA * ld + s];
+  // the parameter rows read after the hot-spot integral: start them towards L1 now
+  {
+    const int later[] = {P_LAI, P_Q, P_B, P_LAT, P_LON, P_SMP, P_SMC, P_PA, P_UO3, P_UH2O, P_DOY};
+#pragma unroll
+    for (int i = 0; i < 11; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(P + later[i] * ld + s));
+  }
+  // uniform geometry: the twelve F loads are issued here, so that their latency overlaps the
+  // volume-scattering classes computed by 13 threads of the block
+  double F[12];
+  if (uniform_geometry) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) F[i] = rec[(size_t)(kRowF + i) * n + s];
+  }
   const double psi = fabs(rel - 360.0 * rint(rel / 360.0));
   const double psi_rad = psi * SPART_DEG2RAD;
   // zenith angles and the folded azimuth are a few radians at most: bounded-range sincos
@@ -457,23 +469,13 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
       s_cls[tid][2] = frho * inv_cc;
       s_cls[tid][3] = ftau * inv_cc;
     }
-    __syncthreads();
   }
+  __syncthreads();
   if (!valid) return;
-  // the parameter rows read after the hot-spot integral: start them towards L1 now
-  {
-    const int later[] = {P_LAI, P_Q, P_B, P_LAT, P_LON, P_SMP, P_SMC, P_PA, P_UO3, P_UH2O, P_DOY};
-#pragma unroll
-    for (int i = 0; i < 11; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(P + later[i] * ld + s));
-  }
 
   // 13 leaf-inclination classes, dotted with lidf (sailh.py:81-97)
   double k = 0.0, K = 0.0, bf = 0.0, sob = 0.0, sof = 0.0;
   if (uniform_geometry) {
-    // all twelve F loads are issued before the first use (one memory latency instead of twelve)
-    double F[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) F[i] = rec[(size_t)(kRowF + i) * n + s];
     double Fprev = 0.0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
