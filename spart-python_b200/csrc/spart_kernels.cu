@@ -369,19 +369,23 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
 constexpr int kRowF = R_COUNT;
 constexpr int kWsRows = R_COUNT + 12;
 
-#ifndef SPART_LIDF_MINBLOCKS
-#define SPART_LIDF_MINBLOCKS 8
+#ifndef SPART_LIDF_THREADS
+#define SPART_LIDF_THREADS 128
 #endif
+#ifndef SPART_LIDF_MINBLOCKS
+#define SPART_LIDF_MINBLOCKS (1024 / SPART_LIDF_THREADS)
+#endif
+constexpr int kLidfThreads = SPART_LIDF_THREADS;
 
 // Kernel 1: leaf inclination distribution (CanopyStructure.__init__, sailh.py:340-398).
 // A kernel of its own so that it runs at ~54 registers / 36 warps per SM: the iteration is
 // one long dependent FP64 chain per lane and needs the occupancy to fill the FP64 pipe.
 // ab0/ab1: the LIDFa / LIDFb rows; F(theta_i) of sample s is written to
 // out[i * stride_ang + s * stride_smp].
-__global__ void __launch_bounds__(kSampleThreads, SPART_LIDF_MINBLOCKS)
+__global__ void __launch_bounds__(kLidfThreads, SPART_LIDF_MINBLOCKS)
 lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t n, double* __restrict__ out,
             int64_t stride_ang, int64_t stride_smp) {
-  constexpr int kWarps = kSampleThreads / 32;
+  constexpr int kWarps = kLidfThreads / 32;
   __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
   __shared__ double sX[kWarps][kLidfTasks];
   __shared__ unsigned char sDone[kWarps][kLidfTasks];
@@ -1302,9 +1306,9 @@ size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n) {
 }
 
 static int launch_lidf(const double* params_dev, int64_t n, int64_t ld, double* ws, cudaStream_t st) {
-  const int64_t per_block = (int64_t)(kSampleThreads / 32) * kLidfSpw;
+  const int64_t per_block = (int64_t)(kLidfThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev + P_LIDFA * ld, params_dev + P_LIDFB * ld, n,
+  lidf_kernel<<<blocks, kLidfThreads, 0, st>>>(params_dev + P_LIDFA * ld, params_dev + P_LIDFB * ld, n,
                                                  ws + (size_t)kRowF * n, n, 1);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -1556,9 +1560,9 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
     int rc = init_device_constants(dev);
     if (rc) return rc;
   }
-  const int64_t per_block = (int64_t)(kSampleThreads / 32) * kLidfSpw;
+  const int64_t per_block = (int64_t)(kLidfThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(ab_dev, ab_dev + ld, n, out_dev, 1, 13);
+  lidf_kernel<<<blocks, kLidfThreads, 0, (cudaStream_t)stream>>>(ab_dev, ab_dev + ld, n, out_dev, 1, 13);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   lidf_diff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, n);
