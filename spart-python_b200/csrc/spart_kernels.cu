@@ -33,11 +33,17 @@ using namespace spart;
 #ifndef SPART_BAND_CHUNK
 #define SPART_BAND_CHUNK 16
 #endif
+#ifndef SPART_BAND_SMEM_STATE
+#define SPART_BAND_SMEM_STATE 1
+#endif
 #ifndef SPART_BAND_MINBLOCKS_U
-#define SPART_BAND_MINBLOCKS_U 4
+#define SPART_BAND_MINBLOCKS_U 5
+#endif
+#ifndef SPART_SRF_MINBLOCKS
+#define SPART_SRF_MINBLOCKS 3
 #endif
 #ifndef SPART_BAND_MINBLOCKS
-#define SPART_BAND_MINBLOCKS 3
+#define SPART_BAND_MINBLOCKS 4
 #endif
 #ifndef SPART_SAMPLE_MINBLOCKS
 #define SPART_SAMPLE_MINBLOCKS 5
@@ -658,8 +664,22 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   if (s >= n) return;
 
   const LeafPar L = load_leaf(P, ld, s);
+#if SPART_BAND_SMEM_STATE
+  // soil and canopy state parked in shared memory (one column per thread, no synchronisation needed)
+  // and re-read per band right before use: 34 registers less live across the leaf model
+  __shared__ double s_st[17][kBandThreads];
+  SoilPar S = load_soil(P, ld, rec, n, s);
+  CanopyGeo G = load_geo(P, ld, rec, n, s);
+  {
+    const double v[17] = {S.f1, S.f2, S.f3, S.mu, S.emu, S.film, G.LAI, G.k, G.K, G.bf, G.sob, G.sof,
+                          G.tau_ss, G.tau_oo, G.sumpso, G.pso2w, G.Z};
+#pragma unroll
+    for (int i = 0; i < 17; ++i) s_st[i][threadIdx.x] = v[i];
+  }
+#else
   const SoilPar S = load_soil(P, ld, rec, n, s);
   const CanopyGeo G = load_geo(P, ld, rec, n, s);
+#endif
   AtmSample A;
   AtmColumn C;
   if (kUniform) {
@@ -701,8 +721,20 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
       const double* lc = &bt[BT_LC0 + pt * LC_COUNT];
       double refl, tran, kchl, rwet, rdry, a0, a1, a2, a3;
       prospect_point<false>(L, lc, &s_tau, refl, tran, kchl);
+#if SPART_BAND_SMEM_STATE
+      {
+        volatile double(*st)[kBandThreads] = s_st;
+        const int t = threadIdx.x;
+        S.f1 = st[0][t]; S.f2 = st[1][t]; S.f3 = st[2][t]; S.mu = st[3][t]; S.emu = st[4][t]; S.film = st[5][t];
+        bsm_point(S, lc, rwet, rdry);
+        G.LAI = st[6][t]; G.k = st[7][t]; G.K = st[8][t]; G.bf = st[9][t]; G.sob = st[10][t]; G.sof = st[11][t];
+        G.tau_ss = st[12][t]; G.tau_oo = st[13][t]; G.sumpso = st[14][t]; G.pso2w = st[15][t]; G.Z = st[16][t];
+        sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
+      }
+#else
       bsm_point(S, lc, rwet, rdry);
       sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
+#endif
       if (pt == 0) {
         rso = a0; rdo = a1; rsd = a2; rdd = a3;
       } else {
@@ -732,7 +764,7 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
 // walked in chunks of kSrfChunk entries whose constants and weights are staged in shared memory.
 constexpr int kSrfChunk = 32;
 
-__global__ void __launch_bounds__(kBandThreads, SPART_BAND_MINBLOCKS)
+__global__ void __launch_bounds__(kBandThreads, SPART_SRF_MINBLOCKS)
 band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
                 const double* __restrict__ band_table, const double* __restrict__ lc_table,
                 const int32_t* __restrict__ srf_idx, const int32_t* __restrict__ srf_len,
