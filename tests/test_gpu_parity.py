@@ -314,6 +314,35 @@ def test_uniform_geometry_flag_is_only_an_optimisation(env):
     assert np.array_equal(c, b)
 
 
+@pytest.mark.parametrize("sensor,n", [("TerraAqua-MODIS", 1000), ("Sentinel3A-OLCI", 777), ("LANDSAT8-OLI", 129),
+                                      ("Sentinel2B-MSI", 1)])
+def test_uniform_geometry_all_band_layouts(env, sensor, n):
+    """The uniform-geometry band kernel (geometry folded into per-band constants once per block)
+    against the general kernel and the oracle: two-knot bands (MODIS, OLCI), more than one band
+    chunk (20 / 21 bands), ragged last tile, single sample; off-nadir, off-principal-plane angles."""
+    torch, sb, so = env
+    P = so.synthetic_params(n, 3, seed=77)
+    P[:, so.SZA], P[:, so.VZA], P[:, so.RAA] = 51.25, 27.5, 97.0
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    a = sb.run_batch_params(dev, sensor).cpu().numpy()
+    b = sb.run_batch_params(dev, sensor, uniform_geometry=True).cpu().numpy()
+    assert relerr(b, a) < 1e-13
+    assert relerr(b, so.spart_bands(P, sensor)) < RTOL64
+
+
+@pytest.mark.parametrize("name", ["cfg2_S2A", "cfg5_S2B"])
+def test_uniform_geometry_vs_reference_golden(env, name):
+    """The fixed-geometry goldens of the unmodified reference through the uniform-geometry path."""
+    torch, sb, _ = env
+    g = load_golden(f"batch_{name}.npz")
+    P = np.asarray(g["params"], dtype=np.float64)
+    assert np.ptp(P[:, 19:22], axis=0).max() == 0.0        # these batches share one geometry
+    dev = torch.from_numpy(np.ascontiguousarray(P.T)).cuda()
+    got = sb.run_batch_params(dev, str(g["sensor"]), uniform_geometry=True).cpu().numpy()
+    assert relerr(got, g["O2"]) < RTOL64
+    assert relerr(got, g["O1"]) < 5e-8
+
+
 def test_cfg4_synthetic_fullspectrum_sensor(env):
     _, sb, so = env
     g = load_golden("batch_cfg4_SYNTH2001.npz")
