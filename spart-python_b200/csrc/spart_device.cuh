@@ -90,9 +90,9 @@ __constant__ double c_gl_w[SPART_NQ] = SPART_GL12_W;
 __constant__ double c_gl6_x[SPART_NQ1] = SPART_GL6_X;
 __constant__ double c_gl6_w[SPART_NQ1] = SPART_GL6_W;
 // 24-point rule for the two wide panels of the hot-spot integral
-#define SPART_NQ2 24
-__constant__ double c_gl24_x[SPART_NQ2] = SPART_GL24_X;
-__constant__ double c_gl24_w[SPART_NQ2] = SPART_GL24_W;
+#define SPART_NQ2 16
+__constant__ double c_glp_x[SPART_NQ2] = SPART_GL16_X;
+__constant__ double c_glp_w[SPART_NQ2] = SPART_GL16_W;
 
 // ---- bounded-range sine / cosine ------------------------------------------------------------
 // |x| is at most a few pi here (leaf-angle iteration), so a two-term Cody-Waite reduction by
@@ -657,12 +657,15 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
 // Here the first integral is split at x = -L, L = min(1, 40/alpha, 40/(A - sqrt(Kk) LAI)):
 //   * below -L either e^{alpha x} < e^-40 (pso is a pure exponential, integrated in closed
 //     form) or pso itself is < e^-40 of its peak (dropped);
-//   * [-L, 0] is covered by SPART_NP = 2 panels of a 24-point Gauss-Legendre rule.  The
-//     integrand is analytic; on a panel its exponent varies by at most ~40 and the high-order
-//     rule resolves it to ~4e-15 (tools/check notes in DESIGN.md: 2 x 24 nodes are as accurate
-//     as 10 x 12 or the reference's 60 x 21).
-// All lanes run the same trip counts (no divergence); cost 96 + 12 exp instead of 557.
+//   * [-L, 0] is covered by two graded panels, [-L/5, 0] and [-L, -L/5], of a 16-point
+//     Gauss-Legendre rule each.  The integrand is analytic and varies fastest next to the hot spot
+//     at x = 0; with the split at L/5 the 32 nodes agree with 16 panels x 24 nodes to 3e-15 on the
+//     benchmark distributions and to 4e-13 for q down to 1e-4, LAI up to 20 and zenith angles up
+//     to 85 degrees (two equal panels of 24 nodes: 2e-15 / 4e-12; the study is described in
+//     DESIGN.md).
+// All lanes run the same trip counts (no divergence); cost 64 + 12 exp instead of 557.
 #define SPART_NP 2
+#define SPART_HOTSPOT_SPLIT 0.2
 __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI, double q, double dso,
                                                   double& sumpso_ilai, double& pso2w) {
   const double A0 = (K + k) * LAI;
@@ -678,22 +681,22 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
   double L = 1.0;
   if (alpha > 0.0) L = fmin(L, 40.0 * rcp_fast(alpha));
   if (Amin > 0.0) L = fmin(L, 40.0 * rcp_fast(Amin));
-  const double h = L * (1.0 / SPART_NP);
   double total = 0.0;
 #pragma unroll 1
   for (int j = 0; j < SPART_NP; ++j) {
-    const double xc = -(j + 0.5) * h;          // panel centre
+    // panel 0 = [-SPLIT L, 0], panel 1 = [-L, -SPLIT L]
+    const double hw = (j == 0 ? 0.5 * SPART_HOTSPOT_SPLIT : 0.5 * (1.0 - SPART_HOTSPOT_SPLIT)) * L;   // half width
+    const double xc = (j == 0 ? -0.5 * SPART_HOTSPOT_SPLIT : -0.5 * (1.0 + SPART_HOTSPOT_SPLIT)) * L;  // centre
     double acc = 0.0;
 #pragma unroll 4
     for (int i = 0; i < SPART_NQ2; ++i) {
-      const double x = fma(0.5 * h, c_gl24_x[i], xc);
+      const double x = fma(hw, c_glp_x[i], xc);
       const double ea = exp_bounded(alpha * x);                 // alpha x in [-40, 0]
       const double arg = fma(A, x, Cq * (1.0 - ea));
-      acc = fma(c_gl24_w[i], exp_bounded(arg), acc);            // arg in [-80, 0]: A L <= 40 A / Amin <= 80
+      acc = fma(c_glp_w[i], exp_bounded(arg), acc);             // arg in [-80, 0]: A L <= 40 A / Amin <= 80
     }
-    total += acc;
+    total = fma(hw, acc, total);
   }
-  total *= 0.5 * h;
   if (L < 1.0 && alpha * L >= 40.0 * (1.0 - 1e-12)) {  // analytic pure-exponential remainder
     total += exp_fast(Cq - A * L) * (1.0 - exp_fast(-A * (1.0 - L))) * rcp_fast(A);
   }
