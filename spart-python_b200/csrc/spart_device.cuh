@@ -81,15 +81,12 @@ __constant__ double c_tau_coef[SPART_TAU_NINT][SPART_TAU_DEG + 1];
 __constant__ double c_tau_mid[SPART_TAU_NINT];
 __constant__ double c_tau_invhalf[SPART_TAU_NINT];
 
-// 12-point Gauss-Legendre rule on [-1, 1] (hot-spot integral)
-#define SPART_NQ 12
-__constant__ double c_gl_x[SPART_NQ] = SPART_GL12_X;
-__constant__ double c_gl_w[SPART_NQ] = SPART_GL12_W;
-// 6-point rule for the narrow last layer of the hot-spot integral
+// Gauss-Legendre rules on [-1, 1] for the hot-spot integral (tools/gen_math_coeffs.py):
+// 6-point rule for the narrow last layer
 #define SPART_NQ1 6
 __constant__ double c_gl6_x[SPART_NQ1] = SPART_GL6_X;
 __constant__ double c_gl6_w[SPART_NQ1] = SPART_GL6_W;
-// 24-point rule for the two wide panels of the hot-spot integral
+// 16-point rule for the two graded panels
 #define SPART_NQ2 16
 __constant__ double c_glp_x[SPART_NQ2] = SPART_GL16_X;
 __constant__ double c_glp_w[SPART_NQ2] = SPART_GL16_W;

@@ -106,6 +106,8 @@ def main():
         return xs, ws
     gl24_x, gl24_w = gauss_legendre(24)
     gl16_x, gl16_w = gauss_legendre(16)
+    gl10_x, gl10_w = gauss_legendre(10)
+    gl4_x, gl4_w = gauss_legendre(4)
     gl6_x, gl6_w = gauss_legendre(6)
     # e^r on |r| <= ln2/2 (+1%): degree-11 Chebyshev interpolant, monomial basis
     rmax = mp.log(2) / 2 * mp.mpf("1.01")
@@ -201,6 +203,10 @@ def main():
         f.write("#define SPART_GL12_W {" + ", ".join(mp.nstr(v, 20) for v in mp_w) + "}\n")
         f.write("#define SPART_GL6_X {" + ", ".join(mp.nstr(v, 20) for v in gl6_x) + "}\n")
         f.write("#define SPART_GL6_W {" + ", ".join(mp.nstr(v, 20) for v in gl6_w) + "}\n")
+        f.write("#define SPART_GL4_X {" + ", ".join(mp.nstr(v, 20) for v in gl4_x) + "}\n")
+        f.write("#define SPART_GL4_W {" + ", ".join(mp.nstr(v, 20) for v in gl4_w) + "}\n")
+        f.write("#define SPART_GL10_X {" + ", ".join(mp.nstr(v, 20) for v in gl10_x) + "}\n")
+        f.write("#define SPART_GL10_W {" + ", ".join(mp.nstr(v, 20) for v in gl10_w) + "}\n")
         f.write("#define SPART_GL16_X {" + ", ".join(mp.nstr(v, 20) for v in gl16_x) + "}\n")
         f.write("#define SPART_GL16_W {" + ", ".join(mp.nstr(v, 20) for v in gl16_w) + "}\n")
         f.write("#define SPART_GL24_X {" + ", ".join(mp.nstr(v, 20) for v in gl24_x) + "}\n")
