@@ -3,11 +3,13 @@
 // Data flow for one batch (all buffers in HBM, struct-of-arrays over samples so that every
 // warp-wide access is one or two fully used 128-byte lines):
 //
-//   params [27][n]  --sample_kernel-->  rec [R_COUNT][n]   (one thread per sample:
-//        leaf-angle distribution, 13-class volume scattering, hot-spot integrals, soil
-//        vector weights, SMAC geometry/pressure scalars, ET scale)
-//   params + rec    --band_kernel---->  out [n][nb][3]      (one thread per (sample, band):
-//        PROSPECT + BSM + SAILH at the 1-2 wavelengths np.interp touches, SMAC, TOC->TOA)
+//   params [27][n]  --lidf_kernel---->  ws rows F_1..F_12 [12][n]   (warp = task queue over
+//        64 samples x 12 angles: the reference's truncated leaf-angle iteration, step for step)
+//   params + F      --geometry_kernel-> rec [R_COUNT][n]   (one thread per sample: 13-class volume
+//        scattering, hot-spot integrals, soil vector weights, SMAC geometry/pressure scalars, ET scale)
+//   params + rec    --band_kernel---->  out [n][nb][3]      (one thread per sample, looping over a
+//        chunk of <= 16 bands: PROSPECT + BSM + SAILH at the 1-2 wavelengths np.interp touches,
+//        SMAC, TOC->TOA; <true> = all samples share the sun / view geometry)
 //   params + rec    --spectrum_kernel-> spec [n][9][2162]   (leafopt/soilopt/canopyopt; thread = wavelength)
 //
 // In band_kernel / spectrum_kernel all lanes of a warp work on the same wavelength, so the
