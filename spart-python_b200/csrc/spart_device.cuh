@@ -255,6 +255,9 @@ __constant__ double c_explog_red[4] = {SPART_LOG2E, 6755399441055744.0, SPART_LN
 #ifndef SPART_EXP_TABLE
 #define SPART_EXP_TABLE 1
 #endif
+#ifndef SPART_EXP_INT_SCALE
+#define SPART_EXP_INT_SCALE 1
+#endif
 __constant__ double c_exp2_tab[64] = SPART_EXP2_TABLE;
 __constant__ double c_expt_poly[4] = SPART_EXPT_POLY;
 __constant__ double c_expt_red[4] = {SPART_64_OVER_LN2, 6755399441055744.0, SPART_LN2_64_HI, SPART_LN2_64_LO};
@@ -291,6 +294,17 @@ __device__ __forceinline__ double exp_core(double x, int& k) {
 #endif
 }
 
+// p * 2^k for p in [0.99, 2) and |k| <= 1011 (the clamped variants): the exponent field is adjusted
+// on the integer pipe instead of a DMUL.  NaN stays NaN: a NaN argument gives the canonical NaN in
+// exp_core's first FMA, whose low word -- and with it k -- is 0.
+__device__ __forceinline__ double exp_scale(double p, int k) {
+#if SPART_EXP_INT_SCALE
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+#else
+  return p * __hiloint2double((k + 1023) << 20, 0);
+#endif
+}
+
 // Full-range exp, branch free: the argument is clamped to [-745.2, 709.8] with NaN-preserving
 // selects (exp(-inf) = 0, exp(+inf) = inf, denormal results rounded correctly by the two-step
 // scaling, NaN in -> NaN out).
@@ -322,7 +336,7 @@ __device__ __forceinline__ double exp_clamp(double x) {
   xc = (x > 700.0) ? 700.0 : xc;
   int k;
   const double p = exp_core(xc, k);
-  return p * __hiloint2double((k + 1023) << 20, 0);
+  return exp_scale(p, k);
 }
 
 // exp_clamp for arguments that are never large and positive (-tau/mu, -m LAI, ...): only the lower
@@ -334,7 +348,7 @@ __device__ __forceinline__ double exp_neg(double x) {
   const double xc = (x < -700.0) ? -700.0 : x;
   int k;
   const double p = exp_core(xc, k);
-  return p * __hiloint2double((k + 1023) << 20, 0);
+  return exp_scale(p, k);
 }
 
 // exp for call sites that guarantee |x| <= 700 for finite inputs (NaN still propagates).
@@ -344,7 +358,7 @@ __device__ __forceinline__ double exp_bounded(double x) {
 #endif
   int k;
   const double p = exp_core(x, k);
-  return p * __hiloint2double((k + 1023) << 20, 0);
+  return exp_scale(p, k);
 }
 
 __device__ __forceinline__ double log_fast(double x) {
