@@ -258,6 +258,9 @@ __constant__ double c_explog_red[4] = {SPART_LOG2E, 6755399441055744.0, SPART_LN
 #ifndef SPART_EXP_INT_SCALE
 #define SPART_EXP_INT_SCALE 1
 #endif
+#ifndef SPART_EXP_INT_CLAMP
+#define SPART_EXP_INT_CLAMP 1
+#endif
 __constant__ double c_exp2_tab[64] = SPART_EXP2_TABLE;
 __constant__ double c_expt_poly[4] = SPART_EXPT_POLY;
 __constant__ double c_expt_red[4] = {SPART_64_OVER_LN2, 6755399441055744.0, SPART_LN2_64_HI, SPART_LN2_64_LO};
@@ -331,9 +334,19 @@ __device__ __forceinline__ double exp_clamp(double x) {
 #if !SPART_FAST_EXP
   return exp(x);
 #endif
+#if SPART_EXP_INT_CLAMP
+  // |x| > 700 (infinities included, NaN excluded) tested and replaced on the high word, integer pipe.
+  // Arguments are arithmetic results, so a NaN is the canonical 0x7ff8... pattern.
+  const int hx = __double2hiint(x);
+  const unsigned ax = (unsigned)hx & 0x7fffffffu;
+  const bool big = (ax - 0x4085E001u) <= (0x7FF00000u - 0x4085E001u);
+  const double xc = __hiloint2double(big ? (int)(0x4085E000u | ((unsigned)hx & 0x80000000u)) : hx,
+                                     big ? 0 : __double2loint(x));
+#else
   double xc = x;
   xc = (x < -700.0) ? -700.0 : xc;
   xc = (x > 700.0) ? 700.0 : xc;
+#endif
   int k;
   const double p = exp_core(xc, k);
   return exp_scale(p, k);
@@ -345,7 +358,15 @@ __device__ __forceinline__ double exp_neg(double x) {
 #if !SPART_FAST_EXP
   return exp(x);
 #endif
+#if SPART_EXP_INT_CLAMP
+  // x < -700 (or -inf) on the high word: as an unsigned number it is then above that of -700.0
+  // (a canonical NaN, 0x7ff8..., is below and passes through)
+  const int hx = __double2hiint(x);
+  const bool big = (unsigned)hx > 0xC085E000u;
+  const double xc = __hiloint2double(big ? (int)0xC085E000u : hx, big ? 0 : __double2loint(x));
+#else
   const double xc = (x < -700.0) ? -700.0 : x;
+#endif
   int k;
   const double p = exp_core(xc, k);
   return exp_scale(p, k);

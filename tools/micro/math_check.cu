@@ -29,6 +29,17 @@ __global__ void eval_kernel(const double* x, int n, double* rc, double* sq, doub
   cs[i] = c;
 }
 
+// special arguments: {NaN, +inf, -inf, 1000, -1000, 700, -700, 0} through exp_clamp / exp_neg / exp_fast
+__global__ void special_kernel(const double* x, int n, double* ec, double* en, double* ef) {
+  exp_table_load();
+  __syncthreads();
+  const int i = threadIdx.x;
+  if (i >= n) return;
+  ec[i] = exp_clamp(x[i] * 1.0);       // arithmetic result, as at every call site
+  en[i] = exp_neg(x[i] * 1.0);
+  ef[i] = exp_fast(x[i] * 1.0);
+}
+
 static double ulps(double got, long double want) {
   if (want == 0.0L) return got == 0.0 ? 0.0 : INFINITY;
   int e;
@@ -72,6 +83,31 @@ int main() {
       worst[4] = std::fmax(worst[4], ulps(h[4][i], sinl(v)));
       worst[5] = std::fmax(worst[5], ulps(h[5][i], cosl(v)));
     }
+  }
+  {
+    const double sp[8] = {NAN, INFINITY, -INFINITY, 1000.0, -1000.0, 700.0, -700.0, 0.0};
+    double *ds, *dr[3], hr[3][8];
+    cudaMalloc(&ds, sizeof(sp));
+    cudaMemcpy(ds, sp, sizeof(sp), cudaMemcpyHostToDevice);
+    for (auto& p : dr) cudaMalloc(&p, sizeof(sp));
+    special_kernel<<<1, 64>>>(ds, 8, dr[0], dr[1], dr[2]);
+    cudaDeviceSynchronize();
+    for (int k = 0; k < 3; ++k) cudaMemcpy(hr[k], dr[k], sizeof(sp), cudaMemcpyDeviceToHost);
+    const char* names[3] = {"exp_clamp", "exp_neg", "exp_fast"};
+    for (int k = 0; k < 3; ++k) {
+      std::fprintf(stderr, "%s:", names[k]);
+      for (int i = 0; i < 8; ++i) std::fprintf(stderr, " f(%g)=%.6g", sp[i], hr[k][i]);
+      std::fprintf(stderr, "\n");
+    }
+    const double e700 = std::exp(700.0), em700 = std::exp(-700.0);
+    bool ok = std::isnan(hr[0][0]) && std::isnan(hr[1][0]) && std::isnan(hr[2][0]);
+    ok = ok && std::fabs(hr[0][1] / e700 - 1) < 1e-14 && std::fabs(hr[0][3] / e700 - 1) < 1e-14;
+    ok = ok && std::fabs(hr[0][2] / em700 - 1) < 1e-14 && std::fabs(hr[0][4] / em700 - 1) < 1e-14;
+    ok = ok && std::fabs(hr[1][2] / em700 - 1) < 1e-14 && std::fabs(hr[1][4] / em700 - 1) < 1e-14;
+    ok = ok && hr[0][7] == 1.0 && hr[1][7] == 1.0 && hr[2][7] == 1.0;
+    ok = ok && std::isinf(hr[2][1]) && hr[2][2] == 0.0 && std::isinf(hr[2][3]) && hr[2][4] == 0.0;
+    std::fprintf(stderr, "special values %s\n", ok ? "ok" : "WRONG");
+    if (!ok) return 2;
   }
   std::printf("{\"n\": %d, \"max_ulp\": {\"rcp_fast\": %.3f, \"sqrt_fast\": %.3f, \"exp_clamp\": %.3f, "
               "\"log_fast\": %.3f, \"sin_small\": %.3f, \"cos_small\": %.3f}}\n",
