@@ -127,6 +127,9 @@ __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
   cs = __hiloint2double(__double2hiint(ca) ^ (((q + 1) & 2) << 30), __double2loint(ca));
 }
 
+// x != 0 for a stored coefficient, tested on the integer pipe (no coefficient is subnormal)
+__device__ __forceinline__ bool nonzero_coef(double x) { return (__double2hiint(x) << 1) != 0; }
+
 // ---- polynomial evaluation -------------------------------------------------------------------
 // poly_eval<DEG, WAYS>: WAYS = 1 is a single Horner chain; WAYS = 2 / 4 evaluate the coefficients
 // of equal index mod WAYS as independent Horner chains in x^WAYS (a few extra operations, 1/WAYS
@@ -405,7 +408,9 @@ __device__ __forceinline__ double log_fast(double x) {
   // special arguments, branch free: +inf / NaN -> x + x, 0 -> -inf, negative -> NaN
   // (positive subnormals are not supported: they return x + x)
   const bool plain = (unsigned)(hi - 0x00100000) < 0x7fe00000u;
-  const double special = (x == 0.0) ? -CUDART_INF : ((x < 0.0) ? CUDART_NAN : x + x);
+  // classified on the bit pattern (integer pipe): +-0 -> -inf, negative -> NaN, +inf / NaN -> x + x
+  const bool zero = (((unsigned)hi << 1) | (unsigned)__double2loint(x)) == 0u;
+  const double special = zero ? -CUDART_INF : ((hi < 0) ? CUDART_NAN : x + x);
   return plain ? res : special;
 }
 
@@ -767,13 +772,13 @@ __device__ __forceinline__ AtmOptics smac_band(const AtmSample& S, const double*
 
   // gaseous transmission, smac.py:105-119
   double gsum = 0.0;
-  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp_clamp(c[SM_NO3] * S.lo3);
-  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp_clamp(c[SM_NH2O] * S.lh2o);
-  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp_clamp(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
-  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp_clamp(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
-  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp_clamp(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
-  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp_clamp(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
-  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp_clamp(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
+  if (nonzero_coef(c[SM_AO3])) gsum += c[SM_AO3] * exp_clamp(c[SM_NO3] * S.lo3);
+  if (nonzero_coef(c[SM_AH2O])) gsum += c[SM_AH2O] * exp_clamp(c[SM_NH2O] * S.lh2o);
+  if (nonzero_coef(c[SM_AO2])) gsum += c[SM_AO2] * exp_clamp(fma(c[SM_NPO2], S.lpeq, c[SM_NO2] * S.lm));
+  if (nonzero_coef(c[SM_ACO2])) gsum += c[SM_ACO2] * exp_clamp(fma(c[SM_NPCO2], S.lpeq, c[SM_NCO2] * S.lm));
+  if (nonzero_coef(c[SM_ACH4])) gsum += c[SM_ACH4] * exp_clamp(fma(c[SM_NPCH4], S.lpeq, c[SM_NCH4] * S.lm));
+  if (nonzero_coef(c[SM_ANO2])) gsum += c[SM_ANO2] * exp_clamp(fma(c[SM_NPNO2], S.lpeq, c[SM_NNO2] * S.lm));
+  if (nonzero_coef(c[SM_ACO])) gsum += c[SM_ACO] * exp_clamp(fma(c[SM_NPCO], S.lpeq, c[SM_NCO] * S.lm));
   const double tg = exp_clamp(gsum);
 
   const double s = c[SM_A0S] * Peq + c[SM_A3S] + c[SM_A1S] * taup550 + c[SM_A2S] * taup550 * taup550;
@@ -945,13 +950,13 @@ __device__ __forceinline__ void smac_toa_band_uniform(const AtmColumn& S, const 
   const double taup = c[SM_A0TAUP] + c[SM_A1TAUP] * taup550;
 
   double gsum = 0.0;
-  if (c[SM_AO3] != 0.0) gsum += c[SM_AO3] * exp_clamp(c[SM_NO3] * S.lo3);
-  if (c[SM_AH2O] != 0.0) gsum += c[SM_AH2O] * exp_clamp(c[SM_NH2O] * S.lh2o);
-  if (c[SM_AO2] != 0.0) gsum += c[SM_AO2] * exp_clamp(fma(c[SM_NPO2], S.lpeq, u[UG_GO2]));
-  if (c[SM_ACO2] != 0.0) gsum += c[SM_ACO2] * exp_clamp(fma(c[SM_NPCO2], S.lpeq, u[UG_GCO2]));
-  if (c[SM_ACH4] != 0.0) gsum += c[SM_ACH4] * exp_clamp(fma(c[SM_NPCH4], S.lpeq, u[UG_GCH4]));
-  if (c[SM_ANO2] != 0.0) gsum += c[SM_ANO2] * exp_clamp(fma(c[SM_NPNO2], S.lpeq, u[UG_GNO2]));
-  if (c[SM_ACO] != 0.0) gsum += c[SM_ACO] * exp_clamp(fma(c[SM_NPCO], S.lpeq, u[UG_GCO]));
+  if (nonzero_coef(c[SM_AO3])) gsum += c[SM_AO3] * exp_clamp(c[SM_NO3] * S.lo3);
+  if (nonzero_coef(c[SM_AH2O])) gsum += c[SM_AH2O] * exp_clamp(c[SM_NH2O] * S.lh2o);
+  if (nonzero_coef(c[SM_AO2])) gsum += c[SM_AO2] * exp_clamp(fma(c[SM_NPO2], S.lpeq, u[UG_GO2]));
+  if (nonzero_coef(c[SM_ACO2])) gsum += c[SM_ACO2] * exp_clamp(fma(c[SM_NPCO2], S.lpeq, u[UG_GCO2]));
+  if (nonzero_coef(c[SM_ACH4])) gsum += c[SM_ACH4] * exp_clamp(fma(c[SM_NPCH4], S.lpeq, u[UG_GCH4]));
+  if (nonzero_coef(c[SM_ANO2])) gsum += c[SM_ANO2] * exp_clamp(fma(c[SM_NPNO2], S.lpeq, u[UG_GNO2]));
+  if (nonzero_coef(c[SM_ACO])) gsum += c[SM_ACO] * exp_clamp(fma(c[SM_NPCO], S.lpeq, u[UG_GCO]));
   const double tg = exp_clamp(gsum);
 
   const double ra_dd = c[SM_A0S] * Peq + c[SM_A3S] + c[SM_A1S] * taup550 + c[SM_A2S] * taup550 * taup550;

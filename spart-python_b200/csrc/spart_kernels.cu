@@ -717,7 +717,7 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
     const double* bt = s_bt[bi];
     // PROSPECT + BSM + SAILH at the one or two wavelengths np.interp touches (SPART.py:220-223)
     double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
-    const int npts = (bt[BT_NPTS] > 1.5) ? 2 : 1;
+    const int npts = (__double2hiint(bt[BT_NPTS]) >= 0x40000000) ? 2 : 1;   // 2.0 or 1.0, integer-pipe test
 #pragma unroll 1
     for (int pt = 0; pt < npts; ++pt) {
       const double* lc = &bt[BT_LC0 + pt * LC_COUNT];
