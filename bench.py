@@ -350,6 +350,7 @@ def run_ours(args):
         "peak_source": "DFMA-chain micro-benchmark measured live in this run (spart_measure_peaks)",
         "kernel_ms": kern_ms, "share_of_step": kern_ms[dominant] / (ms / args.steps),
         "flop_per_simulation": FLOP_PER_SAMPLE, "flop_count_note": flop_note,
+        "kernel_build": kernel_source_sha(),
     }
     nbytes = BYTES_PER_SAMPLE[dominant] * n
     ach_gb = nbytes / (kern_ms[dominant] * 1e-3) / 1e9

@@ -35,7 +35,13 @@ def main(tag):
     flop = {k: v["fp64_flop_per_unit"] for k, v in summ.items()}
     sys.path.insert(0, str(ROOT))
     import bench
-    flop["src_sha"] = bench.kernel_source_sha()     # the counts belong to this kernel build
+    # the counts belong to the kernel build that ran under ncu: take its identity from the bench line
+    # written by the same gpurun call, not from whatever library is in the tree now
+    plain = json.loads((go / f"{tag}_bench_plain.json").read_text().strip().splitlines()[-1])
+    flop["src_sha"] = plain["roofline"].get("kernel_build") or bench.kernel_source_sha()
+    if flop["src_sha"] != bench.kernel_source_sha():
+        print("WARNING: the collected profile belongs to build", flop["src_sha"], "but the tree holds",
+              bench.kernel_source_sha())
     (prof / "flop_per_sample.json").write_text(json.dumps(flop, indent=1) + "\n")
     traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in summ.items()}
     (prof / "dram_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
