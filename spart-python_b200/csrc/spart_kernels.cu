@@ -42,7 +42,7 @@ using namespace spart;
 #define SPART_BAND_MINBLOCKS_U 5
 #endif
 #ifndef SPART_SRF_MINBLOCKS
-#define SPART_SRF_MINBLOCKS 3
+#define SPART_SRF_MINBLOCKS 5
 #endif
 #ifndef SPART_BAND_MINBLOCKS
 #define SPART_BAND_MINBLOCKS 4
@@ -784,8 +784,16 @@ band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   const bool valid = s_raw < n;
   const int64_t s = valid ? s_raw : n - 1;
   const LeafPar L = load_leaf(P, ld, s);
-  const SoilPar S = load_soil(P, ld, rec, n, s);
-  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+  // soil and canopy state parked in a per-thread shared-memory column, as in band_kernel
+  __shared__ double s_st[17][kBandThreads];
+  SoilPar S = load_soil(P, ld, rec, n, s);
+  CanopyGeo G = load_geo(P, ld, rec, n, s);
+  {
+    const double v[17] = {S.f1, S.f2, S.f3, S.mu, S.emu, S.film, G.LAI, G.k, G.K, G.bf, G.sob, G.sof,
+                          G.tau_ss, G.tau_oo, G.sumpso, G.pso2w, G.Z};
+#pragma unroll
+    for (int i = 0; i < 17; ++i) s_st[i][threadIdx.x] = v[i];
+  }
   const int len = srf_len[b];
   const double* wts = srf_w + srf_off[b];
   const int32_t* wix = srf_idx + srf_off[b];
@@ -802,8 +810,15 @@ band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
       const double wj = s_w[j];
       double refl, tran, kchl, rwet, rdry, a0, a1, a2, a3;
       prospect_point<false>(L, s_lc[j], &s_tau, refl, tran, kchl);
-      bsm_point(S, s_lc[j], rwet, rdry);
-      sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
+      {
+        volatile double(*st)[kBandThreads] = s_st;
+        const int t = threadIdx.x;
+        S.f1 = st[0][t]; S.f2 = st[1][t]; S.f3 = st[2][t]; S.mu = st[3][t]; S.emu = st[4][t]; S.film = st[5][t];
+        bsm_point(S, s_lc[j], rwet, rdry);
+        G.LAI = st[6][t]; G.k = st[7][t]; G.K = st[8][t]; G.bf = st[9][t]; G.sob = st[10][t]; G.sof = st[11][t];
+        G.tau_ss = st[12][t]; G.tau_oo = st[13][t]; G.sumpso = st[14][t]; G.pso2w = st[15][t]; G.Z = st[16][t];
+        sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
+      }
       rso = fma(wj, a0, rso);
       rdo = fma(wj, a1, rdo);
       rsd = fma(wj, a2, rsd);
