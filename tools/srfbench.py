@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Timing of the SRF band-convolution mode (band_kernel_srf) on 100 k bench-distribution samples;
+SPART_B200_LIB selects an alternative build of the library.  usage: python tools/srfbench.py"""
 import sys, json, os
 sys.path.insert(0,'/root/repo/spart-python_b200'); sys.path.insert(0,'/root/repo')
 import torch, bench, spart_b200
