@@ -133,8 +133,8 @@ __device__ __forceinline__ bool nonzero_coef(double x) { return (__double2hiint(
 // ---- polynomial evaluation -------------------------------------------------------------------
 // poly_eval<DEG, WAYS>: WAYS = 1 is a single Horner chain; WAYS = 2 / 4 evaluate the coefficients
 // of equal index mod WAYS as independent Horner chains in x^WAYS (a few extra operations, 1/WAYS
-// of the dependency depth) -- the band kernel runs 3 warps per scheduler and is bound by the
-// latency of dependent DFMAs, not by their count.
+// of the dependency depth) -- the band kernels run 4-5 warps per scheduler and lose more to the
+// latency of dependent DFMAs than to their count.
 #ifndef SPART_TAU_SPLIT
 #define SPART_TAU_SPLIT 2
 #endif
@@ -176,8 +176,9 @@ __device__ __forceinline__ double poly_eval(const double* c, double x) {
 // `1.0 / x` compiles to MUFU.RCP64H + 5 DFMA + a range check that branches to an out-of-line
 // fix-up for subnormal / huge operands (~12 instructions and two basic-block boundaries per
 // division).  Every denominator on the band path is a normal number of moderate magnitude, so
-// the seed + two Newton steps suffice: 5 instructions, <= 1 ulp.  0 -> inf/NaN and NaN -> NaN as
-// with a true division; subnormal or > 2^1022 denominators are not supported.
+// the seed (good to ~2^-20) and one third-order step suffice: MUFU + 3 DFMA, 0.51 ulp measured
+// (tools/micro/math_check.cu).  0 -> inf/NaN and NaN -> NaN as with a true division; subnormal or
+// > 2^1022 denominators are not supported.  SPART_RCP_ORDER3 = 0 selects two Newton steps.
 #ifndef SPART_FAST_RCP
 #define SPART_FAST_RCP 1
 #endif
@@ -203,7 +204,7 @@ __device__ __forceinline__ double rcp_fast(double x) {
 #endif
 }
 
-// sqrt from the rsqrt seed and two coupled Newton steps (<= 1 ulp), branch free: sqrt(0) = 0,
+// sqrt from the rsqrt seed and one third-order step (0.76 ulp measured), branch free: sqrt(0) = 0,
 // negative / NaN -> NaN.  (+inf and subnormal arguments are not supported.)
 __device__ __forceinline__ double sqrt_fast(double x) {
 #if !SPART_FAST_RCP
