@@ -183,3 +183,16 @@ def test_sharded_gather_gloo_world2():
     for rank in range(world):
         assert np.array_equal(res[rank][0], want)
     assert np.array_equal(res[0][1], want) and res[1][1] is None
+
+
+@pytest.mark.parametrize("tool,header", [("gen_math_coeffs.py", "math_coeffs.h"), ("gen_tau_coeffs.py", "tau_coeffs.h")])
+def test_generated_coefficient_headers_are_reproducible(tmp_path, tool, header):
+    """The polynomial / quadrature / E1 coefficient headers compiled into the kernels are exactly
+    what their generators produce (multi-precision arithmetic, accuracy asserted inside the tools)."""
+    import subprocess
+    pytest.importorskip("mpmath")
+    out = tmp_path / header
+    subprocess.run([sys.executable, str(ROOT / "tools" / tool), "--out", str(out)], check=True,
+                   capture_output=True, timeout=300)
+    committed = ROOT / "spart-python_b200" / "csrc" / header
+    assert out.read_text() == committed.read_text()

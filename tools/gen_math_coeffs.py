@@ -215,4 +215,7 @@ def main():
 
 
 if __name__ == "__main__":
+    import sys
+    if "--out" in sys.argv:          # write somewhere else (tests compare with the committed header)
+        OUT = Path(sys.argv[sys.argv.index("--out") + 1])
     main()
