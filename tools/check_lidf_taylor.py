@@ -2,7 +2,8 @@
 Taylor model of the map around the hand-over iterate): prints the deviation from the step-by-step
 iteration of the oracle and the iteration counts of both stages for several (TAU, degree) choices."""
 import numpy as np, sys
-sys.path.insert(0,'/root/repo/oracle')
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1] / 'oracle'))
 import spart_oracle as so
 def lidf_two_stage(a,b,tau=2.5e-4,deg=5):
     a=np.asarray(a,float); b=np.asarray(b,float); n=a.size

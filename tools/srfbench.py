@@ -2,7 +2,9 @@
 """Timing of the SRF band-convolution mode (band_kernel_srf) on 100 k bench-distribution samples;
 SPART_B200_LIB selects an alternative build of the library.  usage: python tools/srfbench.py"""
 import sys, json, os
-sys.path.insert(0,'/root/repo/spart-python_b200'); sys.path.insert(0,'/root/repo')
+from pathlib import Path
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / 'spart-python_b200')); sys.path.insert(0, str(ROOT))
 import torch, bench, spart_b200
 dev=torch.device('cuda',0); eng=spart_b200.default_engine(dev)
 n=100000
