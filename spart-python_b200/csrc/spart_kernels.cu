@@ -203,7 +203,7 @@ __device__ __forceinline__ void lidf_poly_setup(double a, double b, double s, do
 #define SPART_LIDF_ASTEPS 2      // exact steps per bookkeeping round
 #endif
 #ifndef SPART_LIDF_BSTEPS
-#define SPART_LIDF_BSTEPS 16     // polynomial steps per bookkeeping round
+#define SPART_LIDF_BSTEPS 20     // polynomial steps per bookkeeping round (best of 12..24)
 #endif
 #ifndef SPART_LIDF_BLOOP
 #define SPART_LIDF_BLOOP 0
