@@ -64,7 +64,9 @@ enum { SPART_FP64 = 64, SPART_FP32 = 32 };
 enum {
   /* the caller guarantees that rows 19..21 (sun / observer angles) are constant over the batch,
    * as in a look-up table for one acquisition geometry; the sample-independent volume-scattering
-   * terms (_volscatt, sailh.py:401-446) are then evaluated once per thread block */
+   * terms (_volscatt, sailh.py:401-446) and the geometry-only sub-expressions of SMAC
+   * (smac.py:125-201) are then evaluated once per thread block instead of once per sample.
+   * Results agree with the general path to a few ulp (sums are re-associated). */
   SPART_FLAG_UNIFORM_GEOMETRY = 1,
   /* the context was created with a user-supplied dry-soil spectrum in row 11 of SpartTables.lc
    * (rows 12, 13 zero): B / lat / lon are ignored and rdry = that spectrum, as with the reference's
