@@ -367,7 +367,7 @@ def run_ours(args):
     cores = host_cores()
     cpu = None
     if not args.no_cpu:
-        rate, ran = time_oracle(512 * cores * 4, cores)
+        rate, ran = time_oracle(512 * cores * 16, cores)     # ~25 core-seconds of oracle work
         cpu = {"value": rate, "unit": "simulations/s", "cores": cores, "kind": "port",
                "sample": f"{ran} samples of the same synthetic distribution, NumPy oracle port "
                          f"(oracle/spart_oracle.py), {cores} processes"}
