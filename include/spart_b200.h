@@ -29,6 +29,16 @@
  *   19..21 angles  sol_angle obs_angle rel_angle, deg  (Angles, sailh.py:298-301)
  *   22..25 atm     aot550 uo3 uh2o Pa                  (AtmosphericProperties, smac.py:307-317)
  *   26     DOY                                         (SPART.__init__, SPART.py:83)
+ *
+ * Broadcast rows: `broadcast_rows` is a bit mask over these 27 rows.  A set bit r says that row r
+ * is constant over the batch (a look-up table with fixed geometry, fixed SMC / film, PROSPECT-5D
+ * without PROT / CBC ...): only params[r * ld + 0] is ever read, the host path copies one element
+ * of that row instead of n, and when bits 19, 20 and 21 are all set -- one sun / observer geometry
+ * for the whole batch BY CONSTRUCTION -- the library evaluates the sample-independent volume
+ * scattering terms (_volscatt, sailh.py:401-446) and the geometry-only sub-expressions of SMAC
+ * (smac.py:125-201) once per thread block instead of once per sample.  Results agree with the
+ * general path to a few ulp (sums are re-associated).  There is no unchecked "the caller promises"
+ * flag: a row is either read per sample or read once.
  */
 #ifndef SPART_B200_H
 #define SPART_B200_H
@@ -40,7 +50,7 @@
 extern "C" {
 #endif
 
-#define SPART_ABI_VERSION 4
+#define SPART_ABI_VERSION 5
 
 #define SPART_NPAR 27       /* rows of a parameter batch                                   */
 #define SPART_NWL 2001      /* 400..2400 nm, 1 nm (SpectralBands.wlP, SPART.py:303)        */
@@ -60,14 +70,9 @@ enum {
 
 enum { SPART_FP64 = 64, SPART_FP32 = 32 };
 
-/* flags of spart_forward_bands */
+/* flags of spart_forward_bands (bit 0 was ABI 4's unchecked uniform-geometry promise; it is now
+ * derived from broadcast_rows and the value 1 is rejected) */
 enum {
-  /* the caller guarantees that rows 19..21 (sun / observer angles) are constant over the batch,
-   * as in a look-up table for one acquisition geometry; the sample-independent volume-scattering
-   * terms (_volscatt, sailh.py:401-446) and the geometry-only sub-expressions of SMAC
-   * (smac.py:125-201) are then evaluated once per thread block instead of once per sample.
-   * Results agree with the general path to a few ulp (sums are re-associated). */
-  SPART_FLAG_UNIFORM_GEOMETRY = 1,
   /* the context was created with a user-supplied dry-soil spectrum in row 11 of SpartTables.lc
    * (rows 12, 13 zero): B / lat / lon are ignored and rdry = that spectrum, as with the reference's
    * SoilParametersFromFile (bsm.py:42-43, 155-226) */
@@ -80,8 +85,21 @@ enum {
    * the same params / n / precision / soil flag (any sensor): skip the per-sample kernels and run
    * only the band kernel.  This is how one batch is evaluated for several sensors (e.g.
    * Sentinel-2A and -2B) while paying for the sensor-independent work once. */
-  SPART_FLAG_REUSE_RECORD = 8
+  SPART_FLAG_REUSE_RECORD = 8,
+  /* SPART_FP32 only: params are float [SPART_NPAR][ld] and the results are written as float, which
+   * halves the bytes on every copy and on the final gather of a sharded run.  The model is
+   * evaluated at the float-rounded inputs. */
+  SPART_FLAG_F32_IO = 16,
+  /* compact result: out = [n][n_bands][2] (R_TOC, R_TOA) followed by etscale[n], the per-sample
+   * extraterrestrial scale cf(DOY) cos(sza) / pi (SPART.py:345-353).  L_TOA is then rebuilt by the
+   * consumer bit for bit as (conv_ea[b] * etscale[s]) * R_TOA[s][b] -- the product the kernels
+   * themselves form (SPART.py:252); conv_ea is the SpartSensor member.  Two thirds of the bytes. */
+  SPART_FLAG_COMPACT_OUT = 32
 };
+
+/* elements of the result buffer of spart_forward_bands for n samples, nb bands and these flags */
+#define SPART_OUT_ELEMS(n, nb, flags) \
+  (((flags) & SPART_FLAG_COMPACT_OUT) ? (size_t)(n) * (size_t)(nb) * 2 + (size_t)(n) : (size_t)(n) * (size_t)(nb) * 3)
 
 typedef struct SpartCtx SpartCtx;
 
@@ -136,29 +154,39 @@ size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n);
 
 /* Replaces the per-sample loop over SPART(...).run() (SPART.py:162-269): for every sample
  * s < n and band b of sensor `sensor`, out_dev[(s * n_bands + b) * 3 + {0,1,2}] =
- * {R_TOC, R_TOA, L_TOA}.  params_dev: [SPART_NPAR][ld] (see top).  precision: SPART_FP64 or
- * SPART_FP32 (arithmetic type of the spectral/atmosphere stage; I/O is always double).
- * Asynchronous on `stream`. */
-int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* params_dev,
-                        int64_t n, int64_t ld, int32_t precision, int32_t flags,
-                        void* workspace_dev, double* out_dev, void* stream);
+ * {R_TOC, R_TOA, L_TOA} (or the compact layout of SPART_FLAG_COMPACT_OUT).  params_dev:
+ * [SPART_NPAR][ld] (see top) of double, or of float with SPART_FLAG_F32_IO; out_dev has the same
+ * element type.  broadcast_rows: see top.  precision: SPART_FP64 or SPART_FP32 (arithmetic type of
+ * the spectral / atmosphere stage).  Asynchronous on `stream`; makes the context's device current
+ * for the duration of the call and restores the caller's. */
+int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_dev,
+                        int64_t n, int64_t ld, uint32_t broadcast_rows, int32_t precision,
+                        int32_t flags, void* workspace_dev, void* out_dev, void* stream);
 
-/* Same computation with HOST buffers: params_host [SPART_NPAR][ld] and out_host
- * [n][n_bands][3] are ordinary (pageable or pinned) host memory; the call stages them
- * through internal pinned buffers in chunks, overlapping H2D, kernels and D2H on internal
- * streams, and returns when out_host is complete.  This is the drop-in for a caller that
- * holds NumPy arrays. */
-int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params_host,
-                             int64_t n, int64_t ld, int32_t precision, int32_t flags,
-                             double* out_host);
+/* Same computation with HOST buffers: params_host [SPART_NPAR][ld] and out_host (layout and
+ * element type as above, SPART_OUT_ELEMS elements) are ordinary host memory.  The batch is cut
+ * into chunks of 64 Ki samples that are pipelined over three internal streams (H2D, kernels,
+ * D2H).  Pinned or registered buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are
+ * DMA'd directly; pageable buffers (plain NumPy arrays) are staged through internal pinned
+ * buffers by a small pool of copy threads (SPART_HOST_THREADS, default 8), because an asynchronous
+ * copy on pageable memory degenerates to a synchronous single-threaded driver copy.  Broadcast
+ * rows move one element.  Returns when out_host is complete; on failure no copy is left in
+ * flight.  This is the drop-in for a caller that holds NumPy arrays. */
+int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_host,
+                             int64_t n, int64_t ld, uint32_t broadcast_rows, int32_t precision,
+                             int32_t flags, void* out_host);
 
 /* Replaces the leafopt / soilopt / canopyopt attributes of a SPART object after run()
  * (SPART.py:192-214, 427-470): full 2162-wavelength spectra.
  * out_dev: double [n][SPART_NSPEC][SPART_NWL_S], planes
  *   0 leaf refl  1 leaf tran  2 kChlrel (0 beyond 2400 nm)  3 soil refl (wet)  4 soil refl dry
- *   (value at 2400 nm beyond)  5 rso  6 rdo  7 rsd  8 rdd. */
+ *   (value at 2400 nm beyond)  5 rso  6 rdo  7 rsd  8 rdd.
+ * rho_thermal / tau_thermal: leaf reflectance / transmittance beyond 2400 nm
+ * (LeafBiology.rho_thermal / tau_thermal, prospect_5d.py:82-83, SPART.py:461-466; the reference's
+ * default is 0.01 each).  flags: 0 or SPART_FLAG_SOIL_SPECTRUM. */
 int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
-                           int32_t flags, void* workspace_dev, double* out_dev, void* stream);
+                           int32_t flags, double rho_thermal, double tau_thermal,
+                           void* workspace_dev, double* out_dev, void* stream);
 
 /* Replaces SMAC(angles, atm, coefs) (smac.py:14-213) for sensor `sensor`.  params_dev:
  * [SPART_NPAR][ld]; only the angle and atmosphere rows 19..25 matter, the others must merely be
@@ -186,11 +214,20 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
  * one output column of spart_forward_bands cast to float) with the smallest weighted squared
  * distance sum_b (sqrt_w[b] (obs_b - lut_b))^2, ties to the lowest index.  weights_dev: sqrt of the
  * band weights [n_bands] or NULL (all 1).  workspace_dev: spart_lut_workspace_bytes(m) bytes.
- * Outputs best_index_dev int32 [m], best_cost_dev float [m]. */
+ * Outputs best_index_dev int64 [m] (= index_offset + local index), best_cost_dev float [m].
+ * Sharded tables: every GPU searches its own slice with index_offset = first global entry of the
+ * slice and packed_dev != NULL; the call then leaves one word (cost bits << 32 | global index)
+ * per observation in packed_dev [m] instead of unpacking it, the caller min-reduces the words
+ * over the GPUs (ncclMin on 64-bit integers: costs are >= 0, so integer order = (cost, index)
+ * order, ties to the lowest global index) and calls spart_lut_unpack.  The full table never has
+ * to be gathered on one GPU.  index_offset + n < 2^32. */
 size_t spart_lut_workspace_bytes(int64_t m);
 int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const float* obs_dev, int64_t m,
-                      const float* weights_dev, void* workspace_dev, int32_t* best_index_dev,
-                      float* best_cost_dev, void* stream);
+                      const float* weights_dev, int64_t index_offset, void* workspace_dev,
+                      int64_t* best_index_dev, float* best_cost_dev, unsigned long long* packed_dev,
+                      void* stream);
+int spart_lut_unpack(const unsigned long long* packed_dev, int64_t m, int64_t* best_index_dev,
+                     float* best_cost_dev, void* stream);
 
 /* Per-kernel timing of spart_forward_bands with CUDA events recorded on the caller's stream
  * (used by bench.py for the roofline).  After spart_profile_enable(ctx, 1) every

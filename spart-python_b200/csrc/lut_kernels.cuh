@@ -22,7 +22,8 @@ constexpr int kLutTile = 128;
 template <int NB4>   // bands padded to 4 * NB4
 __global__ void __launch_bounds__(kLutObs)
 lut_nearest_kernel(const float* __restrict__ lut, int64_t n, int nb, const float* __restrict__ obs, int64_t m,
-                   const float* __restrict__ sqrt_w, int64_t per_slice, unsigned long long* __restrict__ best) {
+                   const float* __restrict__ sqrt_w, int64_t per_slice, unsigned index_offset,
+                   unsigned long long* __restrict__ best) {
   constexpr int NBP = 4 * NB4;
   __shared__ __align__(16) float s_l[kLutTile][NBP];
   __shared__ float s_w[NBP];
@@ -66,17 +67,18 @@ lut_nearest_kernel(const float* __restrict__ lut, int64_t n, int nb, const float
     }
   }
   if (oi < m && best_idx != 0xffffffffu) {
-    const unsigned long long packed = ((unsigned long long)__float_as_uint(best_cost) << 32) | best_idx;
+    // index_offset: position of this LUT (shard) inside a larger table split over several GPUs
+    const unsigned long long packed = ((unsigned long long)__float_as_uint(best_cost) << 32) | (best_idx + index_offset);
     atomicMin(&best[oi], packed);
   }
 }
 
-__global__ void lut_unpack_kernel(const unsigned long long* __restrict__ best, int64_t m, int32_t* __restrict__ idx,
+__global__ void lut_unpack_kernel(const unsigned long long* __restrict__ best, int64_t m, int64_t* __restrict__ idx,
                                   float* __restrict__ cost) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const unsigned long long p = best[i];
-  idx[i] = (int32_t)(p & 0xffffffffu);
+  idx[i] = (int64_t)(p & 0xffffffffu);
   cost[i] = __uint_as_float((unsigned)(p >> 32));
 }
 

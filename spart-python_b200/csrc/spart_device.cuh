@@ -91,6 +91,21 @@ __constant__ double c_gl6_w[SPART_NQ1] = SPART_GL6_W;
 __constant__ double c_glp_x[SPART_NQ2] = SPART_GL16_X;
 __constant__ double c_glp_w[SPART_NQ2] = SPART_GL16_W;
 
+// A parameter batch as the kernels see it: [P_COUNT][ld] of T (double; float with SPART_FLAG_F32_IO).
+// Rows whose bit is set in `bc` are constant over the batch ("broadcast rows"): only their element 0
+// is ever read, which all lanes load from the same address.
+template <typename T>
+struct ParamsT {
+  const T* p;
+  int64_t ld;
+  uint32_t bc;
+  __device__ __forceinline__ const T* ptr(int row, int64_t s) const {
+    return p + row * ld + (((bc >> row) & 1u) ? 0 : s);
+  }
+  __device__ __forceinline__ T at(int row, int64_t s) const { return __ldg(ptr(row, s)); }
+};
+using Params = ParamsT<double>;
+
 // ---- bounded-range sine / cosine ------------------------------------------------------------
 // |x| is at most a few pi here (leaf-angle iteration), so a two-term Cody-Waite reduction by
 // pi/2 is exact to the last bit and no large-argument path is needed.  Accuracy ~1 ulp
@@ -480,17 +495,17 @@ struct LeafPar {
   double Cab, Cca, Cdm, Cw, Cs, Cant, CBC, PROT, N, invN;
 };
 
-__device__ __forceinline__ LeafPar load_leaf(const double* __restrict__ P, int64_t ld, int64_t s) {
+__device__ __forceinline__ LeafPar load_leaf(const Params& P, int64_t s) {
   LeafPar L;
-  L.Cab = P[P_CAB * ld + s];
-  L.Cdm = P[P_CDM * ld + s];
-  L.Cw = P[P_CW * ld + s];
-  L.Cs = P[P_CS * ld + s];
-  L.Cca = P[P_CCA * ld + s];
-  L.Cant = P[P_CANT * ld + s];
-  L.N = P[P_N * ld + s];
-  L.PROT = P[P_PROT * ld + s];
-  L.CBC = P[P_CBC * ld + s];
+  L.Cab = P.at(P_CAB, s);
+  L.Cdm = P.at(P_CDM, s);
+  L.Cw = P.at(P_CW, s);
+  L.Cs = P.at(P_CS, s);
+  L.Cca = P.at(P_CCA, s);
+  L.Cant = P.at(P_CANT, s);
+  L.N = P.at(P_N, s);
+  L.PROT = P.at(P_PROT, s);
+  L.CBC = P.at(P_CBC, s);
   // PROSPECT-PRO switch, prospect_5d.py:148-155
   if ((L.PROT > 0.0 || L.CBC > 0.0) && L.Cdm > 0.0) L.Cdm = 0.0;
   L.invN = rcp_fast(L.N);
@@ -736,7 +751,12 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
     total = fma(hw, acc, total);
   }
   if (L < 1.0 && alpha * L >= 40.0 * (1.0 - 1e-12)) {  // analytic pure-exponential remainder
-    total += exp_fast(Cq - A * L) * (1.0 - exp_fast(-A * (1.0 - L))) * rcp_fast(A);
+    // int_{-1}^{-L} e^{Cq + A x} dx = e^{Cq - A L} (1 - e^{-A (1 - L)}) / A; for A (1 - L) < 1e-4 -- bare
+    // soil, LAI = 0, included -- the quotient is taken from its series (truncation < 5e-14 relative)
+    const double w = 1.0 - L, xr = A * w;
+    const double f = (xr < 1e-4) ? w * fma(xr, fma(xr, 1.0 / 6.0, -0.5), 1.0)
+                                 : (1.0 - exp_fast(-xr)) * rcp_fast(A);
+    total += exp_fast(Cq - A * L) * f;
   }
   sumpso_ilai = total * LAI;
 

@@ -88,17 +88,18 @@ struct LeafParF {
   float Cab, Cca, Cdm, Cw, Cs, Cant, CBC, PROT, N, invN;
 };
 
-__device__ __forceinline__ LeafParF load_leaf_f(const double* __restrict__ P, int64_t ld, int64_t s) {
+template <typename T>
+__device__ __forceinline__ LeafParF load_leaf_f(const ParamsT<T>& P, int64_t s) {
   LeafParF L;
-  L.Cab = (float)P[P_CAB * ld + s];
-  L.Cdm = (float)P[P_CDM * ld + s];
-  L.Cw = (float)P[P_CW * ld + s];
-  L.Cs = (float)P[P_CS * ld + s];
-  L.Cca = (float)P[P_CCA * ld + s];
-  L.Cant = (float)P[P_CANT * ld + s];
-  L.N = (float)P[P_N * ld + s];
-  L.PROT = (float)P[P_PROT * ld + s];
-  L.CBC = (float)P[P_CBC * ld + s];
+  L.Cab = (float)P.at(P_CAB, s);
+  L.Cdm = (float)P.at(P_CDM, s);
+  L.Cw = (float)P.at(P_CW, s);
+  L.Cs = (float)P.at(P_CS, s);
+  L.Cca = (float)P.at(P_CCA, s);
+  L.Cant = (float)P.at(P_CANT, s);
+  L.N = (float)P.at(P_N, s);
+  L.PROT = (float)P.at(P_PROT, s);
+  L.CBC = (float)P.at(P_CBC, s);
   if ((L.PROT > 0.0f || L.CBC > 0.0f) && L.Cdm > 0.0f) L.Cdm = 0.0f;   // prospect_5d.py:148-155
   L.invN = rcp(L.N);
   return L;
@@ -321,7 +322,12 @@ __device__ __forceinline__ void hotspot_integrals_f(float K, float k, float LAI,
     }
     total = fmaf(hw, acc, total);
   }
-  if (L < 1.0f && alpha * L >= 20.0f * (1.0f - 1e-6f)) total += fexp(Cq - A * L) * (1.0f - fexp(-A * (1.0f - L))) * rcp(A);
+  if (L < 1.0f && alpha * L >= 20.0f * (1.0f - 1e-6f)) {
+    // e^{Cq - A L} (1 - e^{-A (1 - L)}) / A, finite for A -> 0 (bare soil): one_minus_exp switches to its series
+    const float w = 1.0f - L, xr = A * w;
+    const float f = (xr < 1e-3f) ? w * fmaf(xr, fmaf(xr, 1.0f / 6.0f, -0.5f), 1.0f) : one_minus_exp(-xr) * rcp(A);
+    total += fexp(Cq - A * L) * f;
+  }
   sumpso_ilai = total * LAI;
   const float dx = 1.0f / 60.0f;
   const float xc = -1.0f - 0.5f * dx;

@@ -17,11 +17,16 @@
 // arithmetic is pure FP64-pipe work; see DESIGN.md for the roofline of each kernel.
 #include <cuda_runtime.h>
 
+#include <nvtx3/nvToolsExt.h>
+
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/spart_b200.h"
@@ -92,6 +97,79 @@ enum BandTableCol {
 __constant__ double c_sin_ttli[13];
 __constant__ double c_cos_ttli[13];
 
+// Small persistent thread pool for the staging copies of the host-buffer path (pageable caller
+// memory <-> pinned staging buffers).  parallel_for(n, f) runs f(0..n-1) on the workers and the
+// calling thread and returns when all are done.
+class HostPool {
+ public:
+  explicit HostPool(int workers) {
+    for (int i = 0; i < workers; ++i) th_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size() + 1; }
+  void parallel_for(int n, const std::function<void(int)>& f) {
+    if (n <= 0) return;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = &f;
+      njobs_ = n;
+      next_ = 0;
+      left_ = n;
+      ++gen_;
+    }
+    cv_work_.notify_all();
+    drain();
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return left_ == 0; });
+    job_ = nullptr;
+  }
+
+ private:
+  void drain() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* f;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!job_ || next_ >= njobs_) return;
+        i = next_++;
+        f = job_;
+      }
+      (*f)(i);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--left_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      drain();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  const std::function<void(int)>* job_ = nullptr;
+  int njobs_ = 0, next_ = 0, left_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
 struct SpartCtx {
   int device = 0;
   int n_sensors = 0;
@@ -104,15 +182,21 @@ struct SpartCtx {
   // the sensor was created without them
   std::vector<int32_t*> d_srf_idx, d_srf_len, d_srf_off;
   std::vector<double*> d_srf_w;
-  // host-buffer path: lazily created staging slots
+  // host-buffer path: lazily created slots (device params / workspace / output, and pinned host
+  // staging buffers that are only allocated when the caller's memory is pageable)
   std::mutex mu;
   static const int kSlots = 3;
   cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
-  double* slot_params[kSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
+  void* slot_params[kSlots] = {nullptr, nullptr, nullptr};
   double* slot_rec[kSlots] = {nullptr, nullptr, nullptr};
-  double* slot_out[kSlots] = {nullptr, nullptr, nullptr};
-  int64_t slot_cap = 0;      // samples per slot
-  int64_t slot_out_cap = 0;  // doubles of output per slot
+  void* slot_out[kSlots] = {nullptr, nullptr, nullptr};
+  void* stage_in[kSlots] = {nullptr, nullptr, nullptr};     // pinned host
+  void* stage_out[kSlots] = {nullptr, nullptr, nullptr};    // pinned host
+  int64_t slot_cap = 0;        // samples per slot
+  size_t slot_out_cap = 0;     // bytes of output per slot
+  size_t stage_in_cap = 0, stage_out_cap = 0;   // bytes
+  HostPool* pool = nullptr;
   // optional per-kernel timing of spart_forward_bands (spart_profile_enable / _read)
   mutable std::mutex prof_mu;
   mutable bool profiling = false;
@@ -125,6 +209,10 @@ struct SpartCtx {
 // kernels
 // --------------------------------------------------------------------------------------
 constexpr int kSampleThreads = 128;
+// internal launch flag (not part of the ABI): rows 19..21 are broadcast rows, i.e. the batch shares one
+// sun / observer geometry by construction
+constexpr int kFlagUniform = 1;
+constexpr uint32_t kGeometryRows = (1u << P_SZA) | (1u << P_VZA) | (1u << P_RAA);
 
 // Leaf inclination distribution for the 32 samples of a warp (sailh.py:351-398).
 // The 32 x 12 (sample, angle) fixed-point iterations need between 1 and ~120 steps each, so
@@ -388,11 +476,11 @@ constexpr int kLidfThreads = SPART_LIDF_THREADS;
 // Kernel 1: leaf inclination distribution (CanopyStructure.__init__, sailh.py:340-398).
 // A kernel of its own so that it runs at ~54 registers / 36 warps per SM: the iteration is
 // one long dependent FP64 chain per lane and needs the occupancy to fill the FP64 pipe.
-// ab0/ab1: the LIDFa / LIDFb rows; F(theta_i) of sample s is written to
-// out[i * stride_ang + s * stride_smp].
+// ab0/ab1: the LIDFa / LIDFb rows with element strides st0/st1 (1, or 0 for a broadcast row);
+// F(theta_i) of sample s is written to out[i * stride_ang + s * stride_smp].
 __global__ void __launch_bounds__(kLidfThreads, SPART_LIDF_MINBLOCKS)
-lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t n, double* __restrict__ out,
-            int64_t stride_ang, int64_t stride_smp) {
+lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t st0, int64_t st1, int64_t n,
+            double* __restrict__ out, int64_t stride_ang, int64_t stride_smp) {
   constexpr int kWarps = kLidfThreads / 32;
   __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
   __shared__ double sX[kWarps][kLidfTasks];
@@ -402,8 +490,8 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
   if (base >= n) return;
   for (int j = lane; j < kLidfSpw; j += 32) {
     const int64_t s = (base + j < n) ? base + j : n - 1;     // tail entries shadow the last sample
-    sA[warp][j] = ab0[s];
-    sB[warp][j] = ab1[s];
+    sA[warp][j] = ab0[s * st0];      // st = 0: the row is constant over the batch (broadcast row)
+    sB[warp][j] = ab1[s * st1];
   }
   __syncwarp();
   const int nvalid = (int)((n - base < kLidfSpw) ? (n - base) : kLidfSpw);
@@ -432,8 +520,8 @@ __global__ void lidf_diff_kernel(double* __restrict__ out, int64_t n) {
 // for one acquisition geometry): the 13-class volume-scattering terms are then evaluated
 // once per block by 13 threads instead of once per sample.
 __global__ void __launch_bounds__(kSampleThreads, SPART_SAMPLE_MINBLOCKS)
-geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __restrict__ rec, int flags) {
-  const int uniform_geometry = flags & SPART_FLAG_UNIFORM_GEOMETRY;
+geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) {
+  const int uniform_geometry = flags & kFlagUniform;
   const bool soil_spectrum = (flags & SPART_FLAG_SOIL_SPECTRUM) != 0;
   __shared__ double s_cls[13][4];   // ksli, koli, sobli, sofli per leaf-inclination class
   exp_table_load();               // published by the barrier below
@@ -443,12 +531,12 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   const int64_t s = valid ? s_raw : n - 1;
 
   // sun / observer geometry (sailh.py:59-78)
-  const double tts = P[P_SZA * ld + s], tto = P[P_VZA * ld + s], rel = P[P_RAA * ld + s];
+  const double tts = P.at(P_SZA, s), tto = P.at(P_VZA, s), rel = P.at(P_RAA, s);
   // the parameter rows read after the hot-spot integral: start them towards L1 now
   {
     const int later[] = {P_LAI, P_Q, P_B, P_LAT, P_LON, P_SMP, P_SMC, P_PA, P_UO3, P_UH2O, P_DOY};
 #pragma unroll
-    for (int i = 0; i < 11; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(P + later[i] * ld + s));
+    for (int i = 0; i < 11; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.ptr(later[i], s)));
   }
   // uniform geometry: the twelve F loads are issued here, so that their latency overlaps the
   // volume-scattering classes computed by 13 threads of the block
@@ -520,7 +608,7 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     }
   }
 
-  const double LAI = P[P_LAI * ld + s], q = P[P_Q * ld + s];
+  const double LAI = P.at(P_LAI, s), q = P.at(P_Q, s);
   double sumpso, pso2w;
   hotspot_integrals(K, k, LAI, q, dso, sumpso, pso2w);
 
@@ -538,16 +626,16 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
 
   // BSM soil-vector weights and Poisson mean (bsm.py:49-51, 101)
   {
-    const double B = P[P_B * ld + s];
+    const double B = P.at(P_B, s);
     double slat, clat, slon, clon;
-    sincos_small(P[P_LAT * ld + s] * SPART_PI / 180.0, slat, clat);
-    sincos_small(P[P_LON * ld + s] * SPART_PI / 180.0, slon, clon);
+    sincos_small(P.at(P_LAT, s) * SPART_PI / 180.0, slat, clat);
+    sincos_small(P.at(P_LON, s) * SPART_PI / 180.0, slon, clon);
     // with a user-supplied dry-soil spectrum (bsm.py:42-43) the context's first soil vector IS that
     // spectrum and the weights are (1, 0, 0): rdry = 1 * spectrum + 0 + 0 exactly
     rec[R_F1 * n + s] = soil_spectrum ? 1.0 : B * slat;
     rec[R_F2 * n + s] = soil_spectrum ? 0.0 : B * clat * slon;
     rec[R_F3 * n + s] = soil_spectrum ? 0.0 : B * clat * clon;
-    const double mu = (P[P_SMP * ld + s] - 5.0) * rcp_fast(P[P_SMC * ld + s]);
+    const double mu = (P.at(P_SMP, s) - 5.0) * rcp_fast(P.at(P_SMC, s));
     rec[R_MU * n + s] = mu;
     rec[R_EMU * n + s] = exp_fast(-mu);
   }
@@ -555,7 +643,7 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   // SMAC per-sample scalars (smac.py:98-102, 129-141)
   {
     const double us = cos_tts, uv = cos_tto;    // cos(tts*cdr), cos(tto*cdr)
-    const double Peq = P[P_PA * ld + s] * (1.0 / 1013.25);
+    const double Peq = P.at(P_PA, s) * (1.0 / 1013.25);
     const double m = inv_cs + inv_co;
     const double crd = 180.0 / SPART_PI;
     double cksi = -((us * uv) + (sqrt(1.0 - us * us) * sqrt(1.0 - uv * uv) * cos(rel * crd)));
@@ -565,8 +653,8 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     rec[R_UV * n + s] = uv;
     rec[R_M * n + s] = m;
     rec[R_PEQ * n + s] = Peq;
-    rec[R_LO3 * n + s] = log_fast(P[P_UO3 * ld + s] * m);
-    rec[R_LH2O * n + s] = log_fast(P[P_UH2O * ld + s] * m);
+    rec[R_LO3 * n + s] = log_fast(P.at(P_UO3, s) * m);
+    rec[R_LH2O * n + s] = log_fast(P.at(P_UH2O, s) * m);
     rec[R_LM * n + s] = log_fast(m);
     rec[R_LPEQ * n + s] = log_fast(Peq);
     rec[R_CKSI * n + s] = cksi;
@@ -578,7 +666,7 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
     rec[R_INV1PUV * n + s] = rcp_fast(1.0 + uv);
     rec[R_AA3 * n + s] = us * uv * rcp_fast(us + uv);
     // extraterrestrial radiance scale (SPART.py:345-353)
-    const double b = 2.0 * SPART_PI * P[P_DOY * ld + s] * (1.0 / 365.0);
+    const double b = 2.0 * SPART_PI * P.at(P_DOY, s) * (1.0 / 365.0);
     double sb, cb, s2b, c2b;
     sincos_small(b, sb, cb);
     sincos_small(2.0 * b, s2b, c2b);
@@ -587,10 +675,10 @@ geometry_kernel(const double* __restrict__ P, int64_t n, int64_t ld, double* __r
   }
 }
 
-__device__ __forceinline__ CanopyGeo load_geo(const double* __restrict__ P, int64_t ld,
+__device__ __forceinline__ CanopyGeo load_geo(const Params& P,
                                               const double* __restrict__ rec, int64_t n, int64_t s) {
   CanopyGeo G;
-  G.LAI = P[P_LAI * ld + s];
+  G.LAI = P.at(P_LAI, s);
   G.k = rec[R_K_SUN * n + s];
   G.K = rec[R_K_OBS * n + s];
   G.bf = rec[R_BF * n + s];
@@ -604,7 +692,7 @@ __device__ __forceinline__ CanopyGeo load_geo(const double* __restrict__ P, int6
   return G;
 }
 
-__device__ __forceinline__ SoilPar load_soil(const double* __restrict__ P, int64_t ld,
+__device__ __forceinline__ SoilPar load_soil(const Params& P,
                                              const double* __restrict__ rec, int64_t n, int64_t s) {
   SoilPar S;
   S.f1 = rec[R_F1 * n + s];
@@ -612,7 +700,7 @@ __device__ __forceinline__ SoilPar load_soil(const double* __restrict__ P, int64
   S.f3 = rec[R_F3 * n + s];
   S.mu = rec[R_MU * n + s];
   S.emu = rec[R_EMU * n + s];
-  S.film = P[P_FILM * ld + s];
+  S.film = P.at(P_FILM, s);
   return S;
 }
 
@@ -628,8 +716,8 @@ constexpr int kBandChunk = SPART_BAND_CHUNK;   // bands handled by one block (pe
 // constants are warp-uniform shared-memory broadcasts.
 template <bool kUniform>
 __global__ void __launch_bounds__(kBandThreads, kUniform ? SPART_BAND_MINBLOCKS_U : SPART_BAND_MINBLOCKS)
-band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
-            const double* __restrict__ band_table, int nb, double* __restrict__ out) {
+band_kernel(const Params P, int64_t n, const double* __restrict__ rec,
+            const double* __restrict__ band_table, int nb, double* __restrict__ out, int compact) {
   __shared__ TauTable s_tau;
   __shared__ double s_bt[kBandChunk][BT_COUNT];
   __shared__ double s_ug[kUniform ? kBandChunk : 1][UG_COUNT];
@@ -665,13 +753,13 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
   if (s >= n) return;
 
-  const LeafPar L = load_leaf(P, ld, s);
+  const LeafPar L = load_leaf(P, s);
 #if SPART_BAND_SMEM_STATE
   // soil and canopy state parked in shared memory (one column per thread, no synchronisation needed)
   // and re-read per band right before use: 34 registers less live across the leaf model
   __shared__ double s_st[17][kBandThreads];
-  SoilPar S = load_soil(P, ld, rec, n, s);
-  CanopyGeo G = load_geo(P, ld, rec, n, s);
+  SoilPar S = load_soil(P, rec, n, s);
+  CanopyGeo G = load_geo(P, rec, n, s);
   {
     const double v[17] = {S.f1, S.f2, S.f3, S.mu, S.emu, S.film, G.LAI, G.k, G.K, G.bf, G.sob, G.sof,
                           G.tau_ss, G.tau_oo, G.sumpso, G.pso2w, G.Z};
@@ -679,8 +767,8 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
     for (int i = 0; i < 17; ++i) s_st[i][threadIdx.x] = v[i];
   }
 #else
-  const SoilPar S = load_soil(P, ld, rec, n, s);
-  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+  const SoilPar S = load_soil(P, rec, n, s);
+  const CanopyGeo G = load_geo(P, rec, n, s);
 #endif
   AtmSample A;
   AtmColumn C;
@@ -689,7 +777,7 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
     C.lo3 = rec[R_LO3 * n + s];
     C.lh2o = rec[R_LH2O * n + s];
     C.lpeq = rec[R_LPEQ * n + s];
-    C.taup550 = P[P_AOT * ld + s];
+    C.taup550 = P.at(P_AOT, s);
   } else {
     A.us = rec[R_US * n + s];
     A.uv = rec[R_UV * n + s];
@@ -702,7 +790,7 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
     A.cksi = rec[R_CKSI * n + s];
     A.ksiD = rec[R_KSID * n + s];
     A.ray_phase = rec[R_RAYPH * n + s];
-    A.taup550 = P[P_AOT * ld + s];
+    A.taup550 = P.at(P_AOT, s);
     A.inv_us = rec[R_INVUS * n + s];
     A.inv_uv = rec[R_INVUV * n + s];
     A.inv_1pus = rec[R_INV1PUS * n + s];
@@ -710,7 +798,10 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
     A.aa3 = rec[R_AA3 * n + s];
   }
   const double etscale = rec[R_ETSCALE * n + s];
-  double* o = out + ((size_t)s * nb + b0) * SPART_NOUT;
+  // full output: [n][nb][3]; compact output (SPART_FLAG_COMPACT_OUT): [n][nb][2] followed by etscale[n]
+  const int nout = compact ? 2 : SPART_NOUT;
+  double* o = out + ((size_t)s * nb + b0) * nout;
+  if (compact && blockIdx.x == 0) out[(size_t)n * nb * 2 + s] = etscale;
 
 #pragma unroll 1
   for (int bi = 0; bi < nbc; ++bi) {
@@ -753,9 +844,9 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
                             L_TOA);
     else
       smac_toa_band(A, &bt[BT_SMAC], bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
-    o[bi * SPART_NOUT + 0] = R_TOC;
-    o[bi * SPART_NOUT + 1] = R_TOA;
-    o[bi * SPART_NOUT + 2] = L_TOA;
+    o[bi * nout + 0] = R_TOC;
+    o[bi * nout + 1] = R_TOA;
+    if (!compact) o[bi * nout + 2] = L_TOA;
   }
 }
 
@@ -767,11 +858,11 @@ band_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
 constexpr int kSrfChunk = 32;
 
 __global__ void __launch_bounds__(kBandThreads, SPART_SRF_MINBLOCKS)
-band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+band_kernel_srf(const Params P, int64_t n, const double* __restrict__ rec,
                 const double* __restrict__ band_table, const double* __restrict__ lc_table,
                 const int32_t* __restrict__ srf_idx, const int32_t* __restrict__ srf_len,
                 const int32_t* __restrict__ srf_off, const double* __restrict__ srf_w, int nb,
-                double* __restrict__ out) {
+                double* __restrict__ out, int compact) {
   __shared__ TauTable s_tau;
   __shared__ double s_bt[BT_COUNT];
   __shared__ double s_lc[kSrfChunk][LC_COUNT];
@@ -783,11 +874,11 @@ band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   const int64_t s_raw = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
   const bool valid = s_raw < n;
   const int64_t s = valid ? s_raw : n - 1;
-  const LeafPar L = load_leaf(P, ld, s);
+  const LeafPar L = load_leaf(P, s);
   // soil and canopy state parked in a per-thread shared-memory column, as in band_kernel
   __shared__ double s_st[17][kBandThreads];
-  SoilPar S = load_soil(P, ld, rec, n, s);
-  CanopyGeo G = load_geo(P, ld, rec, n, s);
+  SoilPar S = load_soil(P, rec, n, s);
+  CanopyGeo G = load_geo(P, rec, n, s);
   {
     const double v[17] = {S.f1, S.f2, S.f3, S.mu, S.emu, S.film, G.LAI, G.k, G.K, G.bf, G.sob, G.sof,
                           G.tau_ss, G.tau_oo, G.sumpso, G.pso2w, G.Z};
@@ -798,6 +889,7 @@ band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   const double* wts = srf_w + srf_off[b];
   const int32_t* wix = srf_idx + srf_off[b];
   double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
+  __syncthreads();      // s_bt / exp table complete even for a band without SRF samples (len == 0)
   for (int c0 = 0; c0 < len; c0 += kSrfChunk) {
     const int m = min(kSrfChunk, len - c0);
     __syncthreads();
@@ -830,21 +922,24 @@ band_kernel_srf(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
   A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s]; A.lpeq = rec[R_LPEQ * n + s];
   A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
-  A.taup550 = P[P_AOT * ld + s];
+  A.taup550 = P.at(P_AOT, s);
   A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
   A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
   double R_TOC, R_TOA, L_TOA;
-  smac_toa_band(A, &s_bt[BT_SMAC], s_bt[BT_CONVEA], rec[R_ETSCALE * n + s], rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
-  double* o = out + ((size_t)s * nb + b) * SPART_NOUT;
+  const double etscale = rec[R_ETSCALE * n + s];
+  smac_toa_band(A, &s_bt[BT_SMAC], s_bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
+  const int nout = compact ? 2 : SPART_NOUT;
+  double* o = out + ((size_t)s * nb + b) * nout;
   o[0] = R_TOC;
   o[1] = R_TOA;
-  o[2] = L_TOA;
+  if (!compact) o[2] = L_TOA;
+  else if (b == 0) out[(size_t)n * nb * 2 + s] = etscale;
 }
 
 // SMAC alone (the reference's SMAC(angles, atm, coefs), smac.py:14-213): the nine
 // AtmosphericOptics arrays per (sample, band); thread = sample, blockIdx.x = band.
 __global__ void __launch_bounds__(kBandThreads)
-smac_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+smac_kernel(const Params P, int64_t n, const double* __restrict__ rec,
             const double* __restrict__ band_table, int nb, double* __restrict__ out) {
   __shared__ double s_c[SM_COUNT];
   const int b = blockIdx.x;
@@ -857,7 +952,7 @@ smac_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
   A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
   A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s]; A.lpeq = rec[R_LPEQ * n + s];
   A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
-  A.taup550 = P[P_AOT * ld + s];
+  A.taup550 = P.at(P_AOT, s);
   A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
   A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
   const AtmOptics O = smac_band(A, s_c);
@@ -877,7 +972,7 @@ smac_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* _
 // sailh.py:14-237): thread = wavelength (coalesced reads of the three input spectra and writes
 // of the four outputs), blockIdx.y = sample; the sample's canopy record is a broadcast load.
 __global__ void __launch_bounds__(256)
-sailh_spectra_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
+sailh_spectra_kernel(const Params P, int64_t n, const double* __restrict__ rec,
                      const double* __restrict__ rs, const double* __restrict__ rho, const double* __restrict__ tau,
                      int64_t stride, int64_t s0, double* __restrict__ out) {
   exp_table_load();
@@ -885,7 +980,7 @@ sailh_spectra_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const 
   const int w = blockIdx.x * 256 + threadIdx.x;
   const int64_t s = s0 + blockIdx.y;
   if (w >= SPART_NWL_S || s >= n) return;
-  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+  const CanopyGeo G = load_geo(P, rec, n, s);
   double rso, rdo, rsd, rdd;
   sailh_point(G, rho[s * stride + w], tau[s * stride + w], rs[s * stride + w], rso, rdo, rsd, rdd);
   double* o = out + (size_t)s * 4 * SPART_NWL_S;
@@ -904,10 +999,11 @@ __constant__ float c_sin_ttli_f[13];
 __constant__ float c_cos_ttli_f[13];
 __constant__ float c_theta2_f[12];
 
+template <typename TIO>
 __global__ void __launch_bounds__(kSampleThreads)
-geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* __restrict__ rec, int flags) {
+geometry_kernel_f32(const ParamsT<TIO> P, int64_t n, float* __restrict__ rec, int flags) {
   using namespace spart::f32;
-  const int uniform_geometry = flags & SPART_FLAG_UNIFORM_GEOMETRY;
+  const int uniform_geometry = flags & kFlagUniform;
   const bool soil_spectrum = (flags & SPART_FLAG_SOIL_SPECTRUM) != 0;
   __shared__ float s_cls[13][4];
   const int tid = threadIdx.x;
@@ -915,7 +1011,7 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
   const bool valid = s_raw < n;
   const int64_t s = valid ? s_raw : n - 1;
 
-  const double tts_d = P[P_SZA * ld + s], tto_d = P[P_VZA * ld + s], rel_d = P[P_RAA * ld + s];
+  const double tts_d = P.at(P_SZA, s), tto_d = P.at(P_VZA, s), rel_d = P.at(P_RAA, s);
   const float tts = (float)tts_d, tto = (float)tto_d, rel = (float)rel_d;
   const float psi = fabsf(rel - 360.0f * rintf(rel / 360.0f));
   const float psi_rad = psi * (SPART_PI_F / 180.0f);
@@ -942,7 +1038,7 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
   }
   if (!valid) return;
 
-  const float a = (float)P[P_LIDFA * ld + s], b = (float)P[P_LIDFB * ld + s];
+  const float a = (float)P.at(P_LIDFA, s), b = (float)P.at(P_LIDFB, s);
   float k = 0.0f, K = 0.0f, bf = 0.0f, sob = 0.0f, sof = 0.0f;
   float Fprev = 0.0f;
 #pragma unroll 1
@@ -966,7 +1062,7 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
     sof += sofli * lidf;
   }
 
-  const float LAI = (float)P[P_LAI * ld + s], q = (float)P[P_Q * ld + s];
+  const float LAI = (float)P.at(P_LAI, s), q = (float)P.at(P_Q, s);
   float sumpso, pso2w;
   hotspot_integrals_f(K, k, LAI, q, dso, sumpso, pso2w);
   const float tau_ss = __expf(-k * LAI), tau_oo = __expf(-K * LAI);
@@ -982,16 +1078,16 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
   rec[R_Z * n + s] = one_minus_exp(-(k + K) * LAI) * rcp(K + k);
 
   {
-    const float B = (float)P[P_B * ld + s];
+    const float B = (float)P.at(P_B, s);
     float slat, clat, slon, clon;
-    sincosf((float)P[P_LAT * ld + s] * (SPART_PI_F / 180.0f), &slat, &clat);
-    sincosf((float)P[P_LON * ld + s] * (SPART_PI_F / 180.0f), &slon, &clon);
+    sincosf((float)P.at(P_LAT, s) * (SPART_PI_F / 180.0f), &slat, &clat);
+    sincosf((float)P.at(P_LON, s) * (SPART_PI_F / 180.0f), &slon, &clon);
     // with a user-supplied dry-soil spectrum (bsm.py:42-43) the context's first soil vector IS that
     // spectrum and the weights are (1, 0, 0): rdry = 1 * spectrum + 0 + 0 exactly
     rec[R_F1 * n + s] = soil_spectrum ? 1.0f : B * slat;
     rec[R_F2 * n + s] = soil_spectrum ? 0.0f : B * clat * slon;
     rec[R_F3 * n + s] = soil_spectrum ? 0.0f : B * clat * clon;
-    const float mu = ((float)P[P_SMP * ld + s] - 5.0f) / (float)P[P_SMC * ld + s];
+    const float mu = ((float)P.at(P_SMP, s) - 5.0f) / (float)P.at(P_SMC, s);
     rec[R_MU * n + s] = mu;
     rec[R_EMU * n + s] = __expf(-mu);
   }
@@ -1003,17 +1099,17 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
     double cksi = -((us_d * uv_d) + (sqrt(1.0 - us_d * us_d) * sqrt(1.0 - uv_d * uv_d) * cos(rel_d * crd)));
     if (cksi < -1.0) cksi = -1.0;
     const float us = (float)us_d, uv = (float)uv_d;
-    const float Peq = (float)(P[P_PA * ld + s] / 1013.25);
+    const float Peq = (float)(P.at(P_PA, s) / 1013.25);
     const float inv_us = rcp(us), inv_uv = rcp(uv);
     const float m = inv_us + inv_uv;
     rec[R_US * n + s] = us;
     rec[R_UV * n + s] = uv;
     rec[R_M * n + s] = m;
     rec[R_PEQ * n + s] = Peq;
-    rec[R_LO3 * n + s] = logf((float)P[P_UO3 * ld + s] * m);
-    rec[R_LH2O * n + s] = logf((float)P[P_UH2O * ld + s] * m);
+    rec[R_LO3 * n + s] = logf((float)P.at(P_UO3, s) * m);
+    rec[R_LH2O * n + s] = logf((float)P.at(P_UH2O, s) * m);
     rec[R_LM * n + s] = logf(m);
-    rec[R_LPEQ * n + s] = (float)log(P[P_PA * ld + s] / 1013.25);   // ln of a number close to 1
+    rec[R_LPEQ * n + s] = (float)log(P.at(P_PA, s) / 1013.25);   // ln of a number close to 1
     rec[R_CKSI * n + s] = (float)cksi;
     rec[R_KSID * n + s] = (float)(crd * acos(cksi));
     rec[R_RAYPH * n + s] = (float)(0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742);
@@ -1022,7 +1118,7 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
     rec[R_INV1PUS * n + s] = rcp(1.0f + us);
     rec[R_INV1PUV * n + s] = rcp(1.0f + uv);
     rec[R_AA3 * n + s] = us * uv * rcp(us + uv);
-    const float bb = 2.0f * SPART_PI_F * (float)P[P_DOY * ld + s] / 365.0f;
+    const float bb = 2.0f * SPART_PI_F * (float)P.at(P_DOY, s) / 365.0f;
     float sb, cb, s2b, c2b;
     sincosf(bb, &sb, &cb);
     sincosf(2.0f * bb, &s2b, &c2b);
@@ -1031,9 +1127,10 @@ geometry_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, float* 
   }
 }
 
+template <typename TIO>
 __global__ void __launch_bounds__(kBandThreads)
-band_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, const float* __restrict__ rec,
-                const double* __restrict__ band_table, int nb, double* __restrict__ out) {
+band_kernel_f32(const ParamsT<TIO> P, int64_t n, const float* __restrict__ rec,
+                const double* __restrict__ band_table, int nb, TIO* __restrict__ out, int compact) {
   using namespace spart::f32;
   __shared__ TauTableF s_tau;
   __shared__ float s_bt[kBandChunk][BT_COUNT];
@@ -1046,12 +1143,12 @@ band_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, const float
   const int64_t s = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
   if (s >= n) return;
 
-  const LeafParF L = load_leaf_f(P, ld, s);
+  const LeafParF L = load_leaf_f(P, s);
   SoilParF S;
   S.f1 = rec[R_F1 * n + s]; S.f2 = rec[R_F2 * n + s]; S.f3 = rec[R_F3 * n + s];
-  S.mu = rec[R_MU * n + s]; S.emu = rec[R_EMU * n + s]; S.film = (float)P[P_FILM * ld + s];
+  S.mu = rec[R_MU * n + s]; S.emu = rec[R_EMU * n + s]; S.film = (float)P.at(P_FILM, s);
   CanopyGeoF G;
-  G.LAI = (float)P[P_LAI * ld + s];
+  G.LAI = (float)P.at(P_LAI, s);
   G.k = rec[R_K_SUN * n + s]; G.K = rec[R_K_OBS * n + s]; G.bf = rec[R_BF * n + s];
   G.sob = rec[R_SOB * n + s]; G.sof = rec[R_SOF * n + s];
   G.tau_ss = rec[R_TAUSS * n + s]; G.tau_oo = rec[R_TAUOO * n + s];
@@ -1060,11 +1157,13 @@ band_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, const float
   A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
   A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s]; A.lpeq = rec[R_LPEQ * n + s];
   A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
-  A.taup550 = (float)P[P_AOT * ld + s];
+  A.taup550 = (float)P.at(P_AOT, s);
   A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
   A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
   const float etscale = rec[R_ETSCALE * n + s];
-  double* o = out + ((size_t)s * nb + b0) * SPART_NOUT;
+  const int nout = compact ? 2 : SPART_NOUT;
+  TIO* o = out + ((size_t)s * nb + b0) * nout;
+  if (compact && blockIdx.x == 0) out[(size_t)n * nb * 2 + s] = (TIO)etscale;
 
 #pragma unroll 1
   for (int bi = 0; bi < nbc; ++bi) {
@@ -1090,9 +1189,9 @@ band_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, const float
     }
     float R_TOC, R_TOA, L_TOA;
     smac_toa_band_f(A, &bt[BT_SMAC], bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
-    o[bi * SPART_NOUT + 0] = (double)R_TOC;
-    o[bi * SPART_NOUT + 1] = (double)R_TOA;
-    o[bi * SPART_NOUT + 2] = (double)L_TOA;
+    o[bi * nout + 0] = (TIO)R_TOC;
+    o[bi * nout + 1] = (TIO)R_TOA;
+    if (!compact) o[bi * nout + 2] = (TIO)L_TOA;
   }
 }
 
@@ -1103,8 +1202,9 @@ band_kernel_f32(const double* __restrict__ P, int64_t n, int64_t ld, const float
 constexpr int kSpecThreads = 256;
 
 __global__ void __launch_bounds__(kSpecThreads)
-spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const double* __restrict__ rec,
-                const double* __restrict__ lc_table, int64_t s0, double* __restrict__ out) {
+spectrum_kernel(const Params P, int64_t n, const double* __restrict__ rec,
+                const double* __restrict__ lc_table, int64_t s0, double rho_thermal, double tau_thermal,
+                double* __restrict__ out) {
   __shared__ TauTable s_tau;
   load_tau_table(&s_tau);
   exp_table_load();
@@ -1112,9 +1212,9 @@ spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   const int w = blockIdx.x * kSpecThreads + threadIdx.x;
   const int64_t s = s0 + blockIdx.y;
   if (w >= SPART_NWL_S || s >= n) return;
-  const LeafPar L = load_leaf(P, ld, s);
-  const SoilPar S = load_soil(P, ld, rec, n, s);
-  const CanopyGeo G = load_geo(P, ld, rec, n, s);
+  const LeafPar L = load_leaf(P, s);
+  const SoilPar S = load_soil(P, rec, n, s);
+  const CanopyGeo G = load_geo(P, rec, n, s);
   double lc[LC_COUNT];
   const int wc = min(w, SPART_NWL - 1);     // thermal wavelengths re-use the 2400 nm soil constants (SPART.py:440)
 #pragma unroll
@@ -1123,9 +1223,9 @@ spectrum_kernel(const double* __restrict__ P, int64_t n, int64_t ld, const doubl
   bsm_point(S, lc, rwet, rdry);
   if (w < SPART_NWL) {
     prospect_point<true>(L, lc, &s_tau, refl, tran, kchl);
-  } else {  // thermal assumptions (SPART.py:461-466; LeafBiology rho/tau_thermal = 0.01)
-    refl = 0.01;
-    tran = 0.01;
+  } else {  // thermal assumptions (SPART.py:461-466): LeafBiology.rho_thermal / tau_thermal
+    refl = rho_thermal;
+    tran = tau_thermal;
     kchl = 0.0;
   }
   sailh_point(G, refl, tran, rwet, rso, rdo, rsd, rdd);
@@ -1182,9 +1282,42 @@ static int time_fma(int sm_count, double* tflops) {
   return SPART_OK;
 }
 
+
 // --------------------------------------------------------------------------------------
 // C ABI
 // --------------------------------------------------------------------------------------
+namespace {
+
+// Makes `device` current for the duration of an entry point and restores the caller's device on
+// exit, so that the library never changes the calling thread's (PyTorch's) current device.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;      // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define GUARD_DEVICE(dev)                                                                  \
+  DeviceGuard _guard(dev);                                                                 \
+  if (_guard.err != cudaSuccess) {                                                         \
+    snprintf(g_err, sizeof(g_err), "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(_guard.err)); \
+    return (int)_guard.err;                                                                \
+  }
+
+// NVTX range around a group of launches (the reference annotates its stages with nvtx,
+// SPART.py:191-227); a no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+}  // namespace
+
 // __constant__ tables are per device: upload them once for every device that is used.
 static int init_device_constants(int device) {
   static std::mutex mu;
@@ -1192,7 +1325,7 @@ static int init_device_constants(int device) {
   std::lock_guard<std::mutex> lock(mu);
   if (device < 0 || device >= 64) return fail(SPART_EINVAL, "device index out of range%s");
   if (done[device]) return SPART_OK;
-  CUDA_TRY(cudaSetDevice(device));
+  GUARD_DEVICE(device);
   CUDA_TRY(cudaMemcpyToSymbol(c_tau_coef, SPART_TAU_COEF_H, sizeof(SPART_TAU_COEF_H)));
   CUDA_TRY(cudaMemcpyToSymbol(c_tau_mid, SPART_TAU_MID_H, sizeof(SPART_TAU_MID_H)));
   CUDA_TRY(cudaMemcpyToSymbol(c_tau_invhalf, SPART_TAU_INVHALF_H, sizeof(SPART_TAU_INVHALF_H)));
@@ -1241,37 +1374,38 @@ int spart_device_count(void) {
   return n;
 }
 
-int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t n_sensors, int32_t device,
-                 SpartCtx** out) {
-  if (!tables || !tables->lc || !out || n_sensors < 0 || (n_sensors > 0 && !sensors))
-    return fail(SPART_EINVAL, "spart_create: null argument%s");
-  if (tables->n_wl != SPART_NWL) return fail(SPART_EINVAL, "spart_create: tables->n_wl must be 2001%s");
-  int ndev = spart_device_count();
-  if (ndev <= 0) return fail(SPART_ENODEV, "spart_create: no CUDA device (this library has no CPU fallback)%s");
-  if (device < 0 || device >= ndev) return fail(SPART_EINVAL, "spart_create: device index out of range%s");
-  for (int i = 0; i < n_sensors; ++i) {
-    const SpartSensor& S = sensors[i];
-    if (S.n_bands <= 0 || !S.wl_lo || !S.wl_hi || !S.wl_frac || !S.smac || !S.conv_ea)
-      return fail(SPART_EINVAL, "spart_create: incomplete sensor%s");
-    for (int b = 0; b < S.n_bands; ++b)
-      if (S.wl_lo[b] < 0 || S.wl_lo[b] >= SPART_NWL || S.wl_hi[b] < S.wl_lo[b] || S.wl_hi[b] >= SPART_NWL)
-        return fail(SPART_EINVAL, "spart_create: band knot outside 400..2400 nm%s");
+int spart_destroy(SpartCtx* ctx) {
+  if (!ctx) return SPART_OK;
+  DeviceGuard guard(ctx->device);
+  for (int i = 0; i < SpartCtx::kSlots; ++i) {
+    if (ctx->streams[i]) cudaStreamSynchronize(ctx->streams[i]);
+    if (ctx->slot_params[i]) cudaFree(ctx->slot_params[i]);
+    if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
+    if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
+    if (ctx->stage_in[i]) cudaFreeHost(ctx->stage_in[i]);
+    if (ctx->stage_out[i]) cudaFreeHost(ctx->stage_out[i]);
+    if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
+    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
   }
-  CUDA_TRY(cudaSetDevice(device));
-  SpartCtx* ctx = new (std::nothrow) SpartCtx();
-  if (!ctx) return fail(SPART_ENOMEM, "spart_create: out of host memory%s");
-  ctx->device = device;
-  ctx->n_sensors = n_sensors;
+  delete ctx->pool;
+  for (auto& pe : ctx->prof_pending) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
+  for (auto& pe : ctx->prof_free) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
+  for (double* d : ctx->d_band) cudaFree(d);
+  for (auto* d : ctx->d_srf_idx) if (d) cudaFree(d);
+  for (auto* d : ctx->d_srf_len) if (d) cudaFree(d);
+  for (auto* d : ctx->d_srf_off) if (d) cudaFree(d);
+  for (auto* d : ctx->d_srf_w) if (d) cudaFree(d);
+  if (ctx->d_lc) cudaFree(ctx->d_lc);
+  delete ctx;
+  return SPART_OK;
+}
+
+// body of spart_create; on any failure the caller releases the partially built context
+static int create_into(SpartCtx* ctx, const SpartTables* tables, const SpartSensor* sensors, int32_t n_sensors,
+                       int32_t device) {
   CUDA_TRY(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
-
-  {
-    int rc = init_device_constants(device);
-    if (rc) {
-      delete ctx;
-      return rc;
-    }
-  }
-
+  int rc = init_device_constants(device);
+  if (rc) return rc;
   const size_t lc_bytes = sizeof(double) * LC_COUNT * SPART_NWL;
   CUDA_TRY(cudaMalloc(&ctx->d_lc, lc_bytes));
   CUDA_TRY(cudaMemcpy(ctx->d_lc, tables->lc, lc_bytes, cudaMemcpyHostToDevice));
@@ -1290,13 +1424,15 @@ int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t 
         row[BT_LC1 + r] = tables->lc[(size_t)r * SPART_NWL + S.wl_hi[b]];
       }
     }
-    double* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, bt.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(d, bt.data(), bt.size() * sizeof(double), cudaMemcpyHostToDevice));
-    ctx->d_band.push_back(d);
+    // every vector gets its slot first, so that spart_destroy releases whatever was allocated
+    ctx->d_band.push_back(nullptr);
     ctx->n_bands.push_back(S.n_bands);
-    int32_t *d_idx = nullptr, *d_len = nullptr, *d_off = nullptr;
-    double* d_w = nullptr;
+    ctx->d_srf_idx.push_back(nullptr);
+    ctx->d_srf_len.push_back(nullptr);
+    ctx->d_srf_off.push_back(nullptr);
+    ctx->d_srf_w.push_back(nullptr);
+    CUDA_TRY(cudaMalloc(&ctx->d_band[i], bt.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(ctx->d_band[i], bt.data(), bt.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (S.srf_idx && S.srf_len && S.srf_w) {
       std::vector<int32_t> off(S.n_bands);
       int64_t total = 0;
@@ -1305,46 +1441,52 @@ int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t 
         off[b] = (int32_t)total;
         total += S.srf_len[b];
       }
-      for (int64_t i = 0; i < total; ++i)
-        if (S.srf_idx[i] < 0 || S.srf_idx[i] >= SPART_NWL)
+      for (int64_t k = 0; k < total; ++k)
+        if (S.srf_idx[k] < 0 || S.srf_idx[k] >= SPART_NWL)
           return fail(SPART_EINVAL, "spart_create: SRF wavelength index outside 400..2400 nm%s");
-      CUDA_TRY(cudaMalloc(&d_idx, sizeof(int32_t) * (total > 0 ? total : 1)));
-      CUDA_TRY(cudaMalloc(&d_len, sizeof(int32_t) * S.n_bands));
-      CUDA_TRY(cudaMalloc(&d_off, sizeof(int32_t) * S.n_bands));
-      CUDA_TRY(cudaMalloc(&d_w, sizeof(double) * (total > 0 ? total : 1)));
-      CUDA_TRY(cudaMemcpy(d_idx, S.srf_idx, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(d_len, S.srf_len, sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(d_off, off.data(), sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(d_w, S.srf_w, sizeof(double) * total, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMalloc(&ctx->d_srf_idx[i], sizeof(int32_t) * (total > 0 ? total : 1)));
+      CUDA_TRY(cudaMalloc(&ctx->d_srf_len[i], sizeof(int32_t) * S.n_bands));
+      CUDA_TRY(cudaMalloc(&ctx->d_srf_off[i], sizeof(int32_t) * S.n_bands));
+      CUDA_TRY(cudaMalloc(&ctx->d_srf_w[i], sizeof(double) * (total > 0 ? total : 1)));
+      CUDA_TRY(cudaMemcpy(ctx->d_srf_idx[i], S.srf_idx, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(ctx->d_srf_len[i], S.srf_len, sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(ctx->d_srf_off[i], off.data(), sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(ctx->d_srf_w[i], S.srf_w, sizeof(double) * total, cudaMemcpyHostToDevice));
     }
-    ctx->d_srf_idx.push_back(d_idx);
-    ctx->d_srf_len.push_back(d_len);
-    ctx->d_srf_off.push_back(d_off);
-    ctx->d_srf_w.push_back(d_w);
   }
-  *out = ctx;
   return SPART_OK;
 }
 
-int spart_destroy(SpartCtx* ctx) {
-  if (!ctx) return SPART_OK;
-  cudaSetDevice(ctx->device);
-  for (int i = 0; i < SpartCtx::kSlots; ++i) {
-    if (ctx->streams[i]) cudaStreamSynchronize(ctx->streams[i]);
-    if (ctx->slot_params[i]) cudaFree(ctx->slot_params[i]);
-    if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
-    if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
-    if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
+int spart_create(const SpartTables* tables, const SpartSensor* sensors, int32_t n_sensors, int32_t device,
+                 SpartCtx** out) {
+  if (!tables || !tables->lc || !out || n_sensors < 0 || (n_sensors > 0 && !sensors))
+    return fail(SPART_EINVAL, "spart_create: null argument%s");
+  if (tables->n_wl != SPART_NWL) return fail(SPART_EINVAL, "spart_create: tables->n_wl must be 2001%s");
+  int ndev = spart_device_count();
+  if (ndev <= 0) return fail(SPART_ENODEV, "spart_create: no CUDA device (this library has no CPU fallback)%s");
+  if (device < 0 || device >= ndev) return fail(SPART_EINVAL, "spart_create: device index out of range%s");
+  for (int i = 0; i < n_sensors; ++i) {
+    const SpartSensor& S = sensors[i];
+    if (S.n_bands <= 0 || !S.wl_lo || !S.wl_hi || !S.wl_frac || !S.smac || !S.conv_ea)
+      return fail(SPART_EINVAL, "spart_create: incomplete sensor%s");
+    for (int b = 0; b < S.n_bands; ++b)
+      if (S.wl_lo[b] < 0 || S.wl_lo[b] >= SPART_NWL || S.wl_hi[b] < S.wl_lo[b] || S.wl_hi[b] >= SPART_NWL)
+        return fail(SPART_EINVAL, "spart_create: band knot outside 400..2400 nm%s");
   }
-  for (auto& pe : ctx->prof_pending) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
-  for (auto& pe : ctx->prof_free) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
-  for (double* d : ctx->d_band) cudaFree(d);
-  for (auto* d : ctx->d_srf_idx) if (d) cudaFree(d);
-  for (auto* d : ctx->d_srf_len) if (d) cudaFree(d);
-  for (auto* d : ctx->d_srf_off) if (d) cudaFree(d);
-  for (auto* d : ctx->d_srf_w) if (d) cudaFree(d);
-  if (ctx->d_lc) cudaFree(ctx->d_lc);
-  delete ctx;
+  GUARD_DEVICE(device);
+  SpartCtx* ctx = new (std::nothrow) SpartCtx();
+  if (!ctx) return fail(SPART_ENOMEM, "spart_create: out of host memory%s");
+  ctx->device = device;
+  ctx->n_sensors = n_sensors;
+  const int rc = create_into(ctx, tables, sensors, n_sensors, device);
+  if (rc) {
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));      // spart_destroy must not disturb the error text
+    spart_destroy(ctx);
+    memcpy(g_err, keep, sizeof(keep));
+    return rc;
+  }
+  *out = ctx;
   return SPART_OK;
 }
 
@@ -1354,47 +1496,86 @@ size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n) {
   return sizeof(double) * (size_t)kWsRows * (size_t)n;
 }
 
-static int launch_lidf(const double* params_dev, int64_t n, int64_t ld, double* ws, cudaStream_t st) {
+static int launch_lidf(const Params& P, int64_t n, double* ws, cudaStream_t st) {
   const int64_t per_block = (int64_t)(kLidfThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel<<<blocks, kLidfThreads, 0, st>>>(params_dev + P_LIDFA * ld, params_dev + P_LIDFB * ld, n,
+  lidf_kernel<<<blocks, kLidfThreads, 0, st>>>(P.p + P_LIDFA * P.ld, P.p + P_LIDFB * P.ld,
+                                                 ((P.bc >> P_LIDFA) & 1u) ? 0 : 1, ((P.bc >> P_LIDFB) & 1u) ? 0 : 1, n,
                                                  ws + (size_t)kRowF * n, n, 1);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
 }
 
-static int launch_geometry(const double* params_dev, int64_t n, int64_t ld, double* ws, int flags,
-                           cudaStream_t st) {
+static int launch_geometry(const Params& P, int64_t n, double* ws, int kflags, cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
-  geometry_kernel<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, ws, flags);
+  geometry_kernel<<<blocks, kSampleThreads, 0, st>>>(P, n, ws, kflags);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
 }
 
-static int check_batch(const SpartCtx* ctx, const void* params, int64_t n, int64_t ld, const void* ws,
+static int check_batch(const SpartCtx* ctx, const void* params, int64_t n, int64_t ld, uint32_t bc, const void* ws,
                        const void* out, const char* who) {
   if (!ctx || !params || !out || (!ws && n > 0)) return fail(SPART_EINVAL, "%s: null argument", who);
   if (n < 0 || ld < n) return fail(SPART_EINVAL, "%s: need 0 <= n <= ld", who);
+  if (bc >> SPART_NPAR) return fail(SPART_EINVAL, "%s: broadcast_rows has bits beyond row 26", who);
   if (n > (int64_t)65535 * kBandThreads)
     return fail(SPART_EINVAL, "%s: n exceeds 65535*128 samples per call; split the batch", who);
   return SPART_OK;
 }
 
-int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* params_dev, int64_t n, int64_t ld,
-                        int32_t precision, int32_t flags, void* workspace_dev, double* out_dev, void* stream) {
-  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_forward_bands");
-  if (rc) return rc;
-  if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "spart_forward_bands: unknown sensor%s");
+static const int kKnownFlags = SPART_FLAG_SOIL_SPECTRUM | SPART_FLAG_SRF_BANDS | SPART_FLAG_REUSE_RECORD |
+                               SPART_FLAG_F32_IO | SPART_FLAG_COMPACT_OUT;
+
+// flag / precision combinations shared by the device and the host entry point
+static int check_mode(const SpartCtx* ctx, int32_t sensor, int32_t precision, int32_t flags, const char* who) {
+  if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "%s: unknown sensor", who);
   if (precision != SPART_FP64 && precision != SPART_FP32)
-    return fail(SPART_EINVAL, "spart_forward_bands: precision must be SPART_FP64 or SPART_FP32%s");
+    return fail(SPART_EINVAL, "%s: precision must be SPART_FP64 or SPART_FP32", who);
+  if (flags & ~kKnownFlags) return fail(SPART_EINVAL, "%s: unknown flag bit", who);
+  if ((flags & SPART_FLAG_F32_IO) && precision != SPART_FP32)
+    return fail(SPART_EINVAL, "%s: SPART_FLAG_F32_IO needs SPART_FP32", who);
   if (flags & SPART_FLAG_SRF_BANDS) {
-    if (precision != SPART_FP64) return fail(SPART_EINVAL, "spart_forward_bands: SRF band mode needs SPART_FP64%s");
-    if (!ctx->d_srf_w[sensor])
-      return fail(SPART_EINVAL, "spart_forward_bands: this sensor was created without SRF tables%s");
+    if (precision != SPART_FP64) return fail(SPART_EINVAL, "%s: SRF band mode needs SPART_FP64", who);
+    if (!ctx->d_srf_w[sensor]) return fail(SPART_EINVAL, "%s: this sensor was created without SRF tables", who);
   }
+  return SPART_OK;
+}
+
+}  // extern "C"
+
+template <typename TIO>
+static int launch_fp32(const SpartCtx* ctx, int sensor, const void* params_dev, int64_t n, int64_t ld, uint32_t bc,
+                       int kflags, bool reuse, bool compact, float* rec, void* out_dev, dim3 grid, cudaStream_t st,
+                       bool prof, const SpartCtx::ProfEvents& pe) {
+  const ParamsT<TIO> P{(const TIO*)params_dev, ld, bc};
+  if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
+  if (!reuse) {
+    NvtxRange r("spart::geometry_f32");
+    const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+    geometry_kernel_f32<TIO><<<blocks, kSampleThreads, 0, st>>>(P, n, rec, kflags);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
+  NvtxRange r("spart::bands_f32");
+  band_kernel_f32<TIO><<<grid, kBandThreads, 0, st>>>(P, n, rec, ctx->d_band[sensor], ctx->n_bands[sensor],
+                                                      (TIO*)out_dev, compact ? 1 : 0);
+  return SPART_OK;
+}
+
+extern "C" {
+
+int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_dev, int64_t n, int64_t ld,
+                        uint32_t broadcast_rows, int32_t precision, int32_t flags, void* workspace_dev, void* out_dev,
+                        void* stream) {
+  int rc = check_batch(ctx, params_dev, n, ld, broadcast_rows, workspace_dev, out_dev, "spart_forward_bands");
+  if (rc) return rc;
+  rc = check_mode(ctx, sensor, precision, flags, "spart_forward_bands");
+  if (rc) return rc;
   if (n == 0) return SPART_OK;
+  GUARD_DEVICE(ctx->device);
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
   SpartCtx::ProfEvents pe;
@@ -1414,40 +1595,46 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const double* param
   const int nb = ctx->n_bands[sensor];
   dim3 grid((unsigned)((nb + kBandChunk - 1) / kBandChunk), (unsigned)((n + kBandThreads - 1) / kBandThreads));
   const bool reuse = (flags & SPART_FLAG_REUSE_RECORD) != 0;   // workspace already holds this batch's record
+  const bool compact = (flags & SPART_FLAG_COMPACT_OUT) != 0;
+  // one sun / observer geometry for the whole batch by construction: rows 19..21 are broadcast rows
+  const bool uniform = (broadcast_rows & kGeometryRows) == kGeometryRows;
+  const int kflags = (flags & SPART_FLAG_SOIL_SPECTRUM) | (uniform ? kFlagUniform : 0);
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
   if (precision == SPART_FP64) {
+    const Params P{(const double*)params_dev, ld, broadcast_rows};
+    double* out = (double*)out_dev;
     if (!reuse) {
-      rc = launch_lidf(params_dev, n, ld, rec, st);
+      NvtxRange r("spart::leaf_angles");
+      rc = launch_lidf(P, n, rec, st);
       if (rc) return rc;
     }
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
     if (!reuse) {
-      rc = launch_geometry(params_dev, n, ld, rec, flags, st);
+      NvtxRange r("spart::geometry");
+      rc = launch_geometry(P, n, rec, kflags, st);
       if (rc) return rc;
     }
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
+    NvtxRange r("spart::bands");
     if (flags & SPART_FLAG_SRF_BANDS) {
       dim3 sgrid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
-      band_kernel_srf<<<sgrid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], ctx->d_lc,
+      band_kernel_srf<<<sgrid, kBandThreads, 0, st>>>(P, n, rec, ctx->d_band[sensor], ctx->d_lc,
                                                       ctx->d_srf_idx[sensor], ctx->d_srf_len[sensor],
-                                                      ctx->d_srf_off[sensor], ctx->d_srf_w[sensor], nb, out_dev);
+                                                      ctx->d_srf_off[sensor], ctx->d_srf_w[sensor], nb, out,
+                                                      compact ? 1 : 0);
+    } else if (uniform) {
+      band_kernel<true><<<grid, kBandThreads, 0, st>>>(P, n, rec, ctx->d_band[sensor], nb, out, compact ? 1 : 0);
     } else {
-      if (flags & SPART_FLAG_UNIFORM_GEOMETRY)
-        band_kernel<true><<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
-      else
-        band_kernel<false><<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+      band_kernel<false><<<grid, kBandThreads, 0, st>>>(P, n, rec, ctx->d_band[sensor], nb, out, compact ? 1 : 0);
     }
   } else {   // SPART_FP32: the leaf angles are solved inside the geometry kernel
-    if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
-    if (!reuse) {
-      const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
-      geometry_kernel_f32<<<blocks, kSampleThreads, 0, st>>>(params_dev, n, ld, (float*)rec, flags);
-      ++g_launches;
-      CUDA_TRY(cudaGetLastError());
-    }
-    if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
-    band_kernel_f32<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, (const float*)rec, ctx->d_band[sensor], nb,
-                                                    out_dev);
+    if (flags & SPART_FLAG_F32_IO)
+      rc = launch_fp32<float>(ctx, sensor, params_dev, n, ld, broadcast_rows, kflags, reuse, compact, (float*)rec,
+                              out_dev, grid, st, prof, pe);
+    else
+      rc = launch_fp32<double>(ctx, sensor, params_dev, n, ld, broadcast_rows, kflags, reuse, compact, (float*)rec,
+                               out_dev, grid, st, prof, pe);
+    if (rc) return rc;
   }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -1470,6 +1657,7 @@ int spart_profile_enable(SpartCtx* ctx, int32_t on) {
 
 int spart_profile_read(SpartCtx* ctx, double* kernel_ms, int64_t* calls) {
   if (!ctx || !kernel_ms || !calls) return fail(SPART_EINVAL, "spart_profile_read: null argument%s");
+  GUARD_DEVICE(ctx->device);
   std::lock_guard<std::mutex> lock(ctx->prof_mu);
   double acc[SPART_NKERNELS] = {0.0, 0.0, 0.0};
   for (auto& pe : ctx->prof_pending) {
@@ -1488,20 +1676,25 @@ int spart_profile_read(SpartCtx* ctx, double* kernel_ms, int64_t* calls) {
 }
 
 int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld, int32_t flags,
-                           void* workspace_dev, double* out_dev, void* stream) {
-  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_forward_spectrum");
+                           double rho_thermal, double tau_thermal, void* workspace_dev, double* out_dev,
+                           void* stream) {
+  int rc = check_batch(ctx, params_dev, n, ld, 0, workspace_dev, out_dev, "spart_forward_spectrum");
   if (rc) return rc;
+  if (flags & ~SPART_FLAG_SOIL_SPECTRUM) return fail(SPART_EINVAL, "spart_forward_spectrum: unknown flag bit%s");
   if (n == 0) return SPART_OK;
+  GUARD_DEVICE(ctx->device);
+  NvtxRange r("spart::spectrum");
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
-  rc = launch_lidf(params_dev, n, ld, rec, st);
+  const Params P{params_dev, ld, 0u};
+  rc = launch_lidf(P, n, rec, st);
   if (rc) return rc;
-  rc = launch_geometry(params_dev, n, ld, rec, flags & ~SPART_FLAG_UNIFORM_GEOMETRY, st);
+  rc = launch_geometry(P, n, rec, flags & SPART_FLAG_SOIL_SPECTRUM, st);
   if (rc) return rc;
   for (int64_t s0 = 0; s0 < n; s0 += 65535) {
     const unsigned ny = (unsigned)((n - s0 < 65535) ? (n - s0) : 65535);
     dim3 grid((SPART_NWL_S + kSpecThreads - 1) / kSpecThreads, ny);
-    spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_lc, s0, out_dev);
+    spectrum_kernel<<<grid, kSpecThreads, 0, st>>>(P, n, rec, ctx->d_lc, s0, rho_thermal, tau_thermal, out_dev);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
   }
@@ -1510,19 +1703,22 @@ int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_
 
 int spart_smac(const SpartCtx* ctx, int32_t sensor, const double* params_dev, int64_t n, int64_t ld,
                void* workspace_dev, double* out_dev, void* stream) {
-  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_smac");
+  int rc = check_batch(ctx, params_dev, n, ld, 0, workspace_dev, out_dev, "spart_smac");
   if (rc) return rc;
   if (sensor < 0 || sensor >= ctx->n_sensors) return fail(SPART_EINVAL, "spart_smac: unknown sensor%s");
   if (n == 0) return SPART_OK;
+  GUARD_DEVICE(ctx->device);
+  NvtxRange r("spart::smac");
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
-  rc = launch_lidf(params_dev, n, ld, rec, st);
+  const Params P{params_dev, ld, 0u};
+  rc = launch_lidf(P, n, rec, st);
   if (rc) return rc;
-  rc = launch_geometry(params_dev, n, ld, rec, 0, st);
+  rc = launch_geometry(P, n, rec, 0, st);
   if (rc) return rc;
   const int nb = ctx->n_bands[sensor];
   dim3 grid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
-  smac_kernel<<<grid, kBandThreads, 0, st>>>(params_dev, n, ld, rec, ctx->d_band[sensor], nb, out_dev);
+  smac_kernel<<<grid, kBandThreads, 0, st>>>(P, n, rec, ctx->d_band[sensor], nb, out_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
@@ -1531,22 +1727,25 @@ int spart_smac(const SpartCtx* ctx, int32_t sensor, const double* params_dev, in
 int spart_sailh(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld, const double* soil_refl_dev,
                 const double* leaf_refl_dev, const double* leaf_tran_dev, int64_t spectra_stride,
                 void* workspace_dev, double* out_dev, void* stream) {
-  int rc = check_batch(ctx, params_dev, n, ld, workspace_dev, out_dev, "spart_sailh");
+  int rc = check_batch(ctx, params_dev, n, ld, 0, workspace_dev, out_dev, "spart_sailh");
   if (rc) return rc;
   if (!soil_refl_dev || !leaf_refl_dev || !leaf_tran_dev) return fail(SPART_EINVAL, "spart_sailh: null spectrum%s");
   if (spectra_stride != 0 && spectra_stride < SPART_NWL_S)
     return fail(SPART_EINVAL, "spart_sailh: spectra_stride must be 0 (shared spectra) or >= 2162%s");
   if (n == 0) return SPART_OK;
+  GUARD_DEVICE(ctx->device);
+  NvtxRange r("spart::sailh");
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
-  rc = launch_lidf(params_dev, n, ld, rec, st);
+  const Params P{params_dev, ld, 0u};
+  rc = launch_lidf(P, n, rec, st);
   if (rc) return rc;
-  rc = launch_geometry(params_dev, n, ld, rec, 0, st);
+  rc = launch_geometry(P, n, rec, 0, st);
   if (rc) return rc;
   for (int64_t s0 = 0; s0 < n; s0 += 65535) {
     const unsigned ny = (unsigned)((n - s0 < 65535) ? (n - s0) : 65535);
     dim3 grid((SPART_NWL_S + 255) / 256, ny);
-    sailh_spectra_kernel<<<grid, 256, 0, st>>>(params_dev, n, ld, rec, soil_refl_dev, leaf_refl_dev, leaf_tran_dev,
+    sailh_spectra_kernel<<<grid, 256, 0, st>>>(P, n, rec, soil_refl_dev, leaf_refl_dev, leaf_tran_dev,
                                                spectra_stride, s0, out_dev);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -1557,15 +1756,22 @@ int spart_sailh(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_
 size_t spart_lut_workspace_bytes(int64_t m) { return m > 0 ? sizeof(unsigned long long) * (size_t)m : 0; }
 
 int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const float* obs_dev, int64_t m,
-                      const float* weights_dev, void* workspace_dev, int32_t* best_index_dev, float* best_cost_dev,
-                      void* stream) {
-  if (!lut_dev || !obs_dev || !best_index_dev || !best_cost_dev || (!workspace_dev && m > 0))
+                      const float* weights_dev, int64_t index_offset, void* workspace_dev, int64_t* best_index_dev,
+                      float* best_cost_dev, unsigned long long* packed_dev, void* stream) {
+  if (!lut_dev || !obs_dev || (!workspace_dev && m > 0))
     return fail(SPART_EINVAL, "spart_lut_nearest: null argument%s");
-  if (n <= 0 || n > 0x7fffffffLL || m < 0 || n_bands < 1 || n_bands > 32)
-    return fail(SPART_EINVAL, "spart_lut_nearest: need 1 <= n < 2^31, m >= 0, 1 <= n_bands <= 32%s");
+  if (!packed_dev && (!best_index_dev || !best_cost_dev))
+    return fail(SPART_EINVAL, "spart_lut_nearest: need best_index_dev + best_cost_dev or packed_dev%s");
+  if (n <= 0 || n > 0x7fffffffLL || m < 0 || n_bands < 1 || n_bands > 32 || index_offset < 0 ||
+      index_offset + n > 0xffffffffLL)
+    return fail(SPART_EINVAL,
+                "spart_lut_nearest: need 1 <= n < 2^31, m >= 0, 1 <= n_bands <= 32, index_offset + n < 2^32%s");
   if (m == 0) return SPART_OK;
+  NvtxRange r("spart::lut_nearest");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned long long* best = (unsigned long long*)workspace_dev;
+  // with packed_dev the (cost, index) words are the result (a sharded search min-reduces them across
+  // GPUs before unpacking); otherwise they live in the workspace
+  unsigned long long* best = packed_dev ? packed_dev : (unsigned long long*)workspace_dev;
   CUDA_TRY(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * m, st));
   int dev = 0, sms = 148;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -1584,7 +1790,8 @@ int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const fl
   const int nb4 = (n_bands + 3) / 4;
 #define SPART_LUT_CASE(K)                                                                                          \
   case K:                                                                                                          \
-    lut_nearest_kernel<K><<<grid, kLutObs, 0, st>>>(lut_dev, n, n_bands, obs_dev, m, weights_dev, per_slice, best); \
+    lut_nearest_kernel<K><<<grid, kLutObs, 0, st>>>(lut_dev, n, n_bands, obs_dev, m, weights_dev, per_slice,       \
+                                                    (unsigned)index_offset, best);                                 \
     break;
   switch (nb4) {
     SPART_LUT_CASE(1) SPART_LUT_CASE(2) SPART_LUT_CASE(3) SPART_LUT_CASE(4)
@@ -1593,7 +1800,21 @@ int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const fl
 #undef SPART_LUT_CASE
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
-  lut_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(best, m, best_index_dev, best_cost_dev);
+  if (best_index_dev && best_cost_dev && !packed_dev) {
+    lut_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(best, m, best_index_dev, best_cost_dev);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return SPART_OK;
+}
+
+int spart_lut_unpack(const unsigned long long* packed_dev, int64_t m, int64_t* best_index_dev, float* best_cost_dev,
+                     void* stream) {
+  if (!packed_dev || !best_index_dev || !best_cost_dev || m < 0)
+    return fail(SPART_EINVAL, "spart_lut_unpack: bad argument%s");
+  if (m == 0) return SPART_OK;
+  lut_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(packed_dev, m, best_index_dev,
+                                                                                   best_cost_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return SPART_OK;
@@ -1609,9 +1830,10 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
     int rc = init_device_constants(dev);
     if (rc) return rc;
   }
+  NvtxRange r("spart::leaf_angles");
   const int64_t per_block = (int64_t)(kLidfThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel<<<blocks, kLidfThreads, 0, (cudaStream_t)stream>>>(ab_dev, ab_dev + ld, n, out_dev, 1, 13);
+  lidf_kernel<<<blocks, kLidfThreads, 0, (cudaStream_t)stream>>>(ab_dev, ab_dev + ld, 1, 1, n, out_dev, 1, 13);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   lidf_diff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out_dev, n);
@@ -1620,42 +1842,89 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
   return SPART_OK;
 }
 
-static int ensure_slots(SpartCtx* ctx, int64_t chunk, int nb) {
-  const int64_t out_need = chunk * nb * SPART_NOUT;
-  if (ctx->slot_cap >= chunk && ctx->slot_out_cap >= out_need) return SPART_OK;
+// ---- host-buffer path ---------------------------------------------------------------------
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_slots(SpartCtx* ctx, int64_t chunk, size_t out_bytes, bool stage_in, bool stage_out) {
+  const size_t in_bytes = sizeof(double) * P_COUNT * (size_t)chunk;
   for (int i = 0; i < SpartCtx::kSlots; ++i) {
     if (!ctx->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
+    if (!ctx->slot_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamSynchronize(ctx->streams[i]));
     if (ctx->slot_cap < chunk) {
       if (ctx->slot_params[i]) cudaFree(ctx->slot_params[i]);
       if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
-      ctx->slot_params[i] = ctx->slot_rec[i] = nullptr;
-      CUDA_TRY(cudaMalloc(&ctx->slot_params[i], sizeof(double) * P_COUNT * chunk));
+      ctx->slot_params[i] = nullptr;
+      ctx->slot_rec[i] = nullptr;
+      CUDA_TRY(cudaMalloc(&ctx->slot_params[i], in_bytes));
       CUDA_TRY(cudaMalloc(&ctx->slot_rec[i], sizeof(double) * kWsRows * chunk));
     }
-    if (ctx->slot_out_cap < out_need) {
+    if (ctx->slot_out_cap < out_bytes) {
       if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
       ctx->slot_out[i] = nullptr;
-      CUDA_TRY(cudaMalloc(&ctx->slot_out[i], sizeof(double) * out_need));
+      CUDA_TRY(cudaMalloc(&ctx->slot_out[i], out_bytes));
+    }
+    if (stage_in && ctx->stage_in_cap < in_bytes) {
+      if (ctx->stage_in[i]) cudaFreeHost(ctx->stage_in[i]);
+      ctx->stage_in[i] = nullptr;
+      CUDA_TRY(cudaHostAlloc(&ctx->stage_in[i], in_bytes, cudaHostAllocDefault));
+    }
+    if (stage_out && ctx->stage_out_cap < out_bytes) {
+      if (ctx->stage_out[i]) cudaFreeHost(ctx->stage_out[i]);
+      ctx->stage_out[i] = nullptr;
+      CUDA_TRY(cudaHostAlloc(&ctx->stage_out[i], out_bytes, cudaHostAllocDefault));
     }
   }
   if (ctx->slot_cap < chunk) ctx->slot_cap = chunk;
-  if (ctx->slot_out_cap < out_need) ctx->slot_out_cap = out_need;
+  if (ctx->slot_out_cap < out_bytes) ctx->slot_out_cap = out_bytes;
+  if (stage_in && ctx->stage_in_cap < in_bytes) ctx->stage_in_cap = in_bytes;
+  if (stage_out && ctx->stage_out_cap < out_bytes) ctx->stage_out_cap = out_bytes;
+  if ((stage_in || stage_out) && !ctx->pool) {
+    int want = 8;
+    if (const char* e = getenv("SPART_HOST_THREADS")) want = atoi(e);
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && want > hw) want = hw;
+    if (want < 1) want = 1;
+    ctx->pool = new (std::nothrow) HostPool(want - 1);
+    if (!ctx->pool) return fail(SPART_ENOMEM, "spart_forward_bands_host: out of host memory%s");
+  }
   return SPART_OK;
 }
 
-int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params_host, int64_t n, int64_t ld,
-                             int32_t precision, int32_t flags, double* out_host) {
-  if (!ctx || !params_host || !out_host) return fail(SPART_EINVAL, "spart_forward_bands_host: null argument%s");
-  if (n < 0 || ld < n) return fail(SPART_EINVAL, "spart_forward_bands_host: need 0 <= n <= ld%s");
-  if (sensor < 0 || sensor >= ctx->n_sensors)
-    return fail(SPART_EINVAL, "spart_forward_bands_host: unknown sensor%s");
-  if (precision != SPART_FP64 && precision != SPART_FP32)
-    return fail(SPART_EINVAL, "spart_forward_bands_host: precision must be SPART_FP64 or SPART_FP32%s");
+// memcpy of `bytes` split into ~1 MiB pieces over the pool
+static void pool_memcpy(HostPool* pool, void* dst, const void* src, size_t bytes) {
+  const size_t piece = (size_t)1 << 20;
+  const int n = (int)((bytes + piece - 1) / piece);
+  pool->parallel_for(n, [&](int i) {
+    const size_t o = (size_t)i * piece;
+    memcpy((char*)dst + o, (const char*)src + o, (bytes - o < piece) ? bytes - o : piece);
+  });
+}
+
+int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_host, int64_t n, int64_t ld,
+                             uint32_t broadcast_rows, int32_t precision, int32_t flags, void* out_host) {
+  const char* who = "spart_forward_bands_host";
+  if (!ctx || !params_host || !out_host) return fail(SPART_EINVAL, "%s: null argument", who);
+  if (n < 0 || ld < n) return fail(SPART_EINVAL, "%s: need 0 <= n <= ld", who);
+  if (broadcast_rows >> SPART_NPAR) return fail(SPART_EINVAL, "%s: broadcast_rows has bits beyond row 26", who);
+  if (flags & SPART_FLAG_REUSE_RECORD) return fail(SPART_EINVAL, "%s: SPART_FLAG_REUSE_RECORD is a device-path flag", who);
+  int rc = check_mode(ctx, sensor, precision, flags, who);
+  if (rc) return rc;
   if (n == 0) return SPART_OK;
   std::lock_guard<std::mutex> lock(ctx->mu);
-  CUDA_TRY(cudaSetDevice(ctx->device));
+  GUARD_DEVICE(ctx->device);
+  NvtxRange range("spart::forward_bands_host");
   const int nb = ctx->n_bands[sensor];
+  const size_t elt = (flags & SPART_FLAG_F32_IO) ? sizeof(float) : sizeof(double);
+  const bool compact = (flags & SPART_FLAG_COMPACT_OUT) != 0;
+  const int nout = compact ? 2 : SPART_NOUT;
   // chunk so that three slots pipeline H2D / kernels / D2H (64 Ki samples: ~14 MB in, ~20 MB out
   // per chunk for 13 bands, small enough that pipeline fill/drain is a few percent of a 1M batch);
   // cap the per-slot output at ~256 MB for many-band sensors
@@ -1663,29 +1932,117 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const double* params
   const int64_t cap_by_out = ((int64_t)256 << 20) / ((int64_t)nb * SPART_NOUT * 8);
   if (chunk > cap_by_out) chunk = cap_by_out > 1024 ? cap_by_out : 1024;
   if (chunk > n) chunk = n;
-  int rc = ensure_slots(ctx, chunk, nb);
+  // pageable caller memory is staged through pinned buffers by the copy threads (a cudaMemcpyAsync on
+  // pageable memory is a synchronous single-threaded driver copy); pinned or registered memory is
+  // DMA'd directly
+  const bool stage_in = !is_pinned_host(params_host), stage_out = !is_pinned_host(out_host);
+  const size_t out_chunk_bytes = ((size_t)chunk * nb * nout + (compact ? (size_t)chunk : 0)) * elt;
+  rc = ensure_slots(ctx, chunk, out_chunk_bytes, stage_in, stage_out);
   if (rc) return rc;
-  int slot = 0;
-  for (int64_t s0 = 0; s0 < n; s0 += chunk, slot = (slot + 1) % SpartCtx::kSlots) {
-    const int64_t m = (n - s0 < chunk) ? (n - s0) : chunk;
-    cudaStream_t st = ctx->streams[slot];
-    // rows of the SoA batch are ld apart on the host and m apart in the slot
-    CUDA_TRY(cudaMemcpy2DAsync(ctx->slot_params[slot], sizeof(double) * m, params_host + s0, sizeof(double) * ld,
-                               sizeof(double) * m, P_COUNT, cudaMemcpyHostToDevice, st));
-    rc = spart_forward_bands(ctx, sensor, ctx->slot_params[slot], m, m, precision, flags, ctx->slot_rec[slot],
-                             ctx->slot_out[slot], st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_host + (size_t)s0 * nb * SPART_NOUT, ctx->slot_out[slot],
-                             sizeof(double) * m * nb * SPART_NOUT, cudaMemcpyDeviceToHost, st));
+  const char* pin = (const char*)params_host;
+  char* pout = (char*)out_host;
+  char* pets = pout + (size_t)n * nb * 2 * elt;      // compact output: etscale[n] follows [n][nb][2]
+
+  struct Pending { int64_t s0 = 0, m = 0; bool live = false; } pend[SpartCtx::kSlots];
+  // wait for a slot's chunk (its staging buffers may then be reused) and, with a pageable output,
+  // copy the chunk from the pinned staging buffer into the caller's array
+  auto unstage = [&](int slot) -> int {
+    Pending& q = pend[slot];
+    if (!q.live) return SPART_OK;
+    q.live = false;
+    CUDA_TRY(cudaEventSynchronize(ctx->slot_done[slot]));
+    if (!stage_out) return SPART_OK;
+    const size_t main_bytes = (size_t)q.m * nb * nout * elt;
+    pool_memcpy(ctx->pool, pout + (size_t)q.s0 * nb * nout * elt, ctx->stage_out[slot], main_bytes);
+    if (compact) memcpy(pets + (size_t)q.s0 * elt, (char*)ctx->stage_out[slot] + main_bytes, (size_t)q.m * elt);
+    return SPART_OK;
+  };
+  auto run = [&]() -> int {
+    int slot = 0, prev = -1;
+    for (int64_t s0 = 0; s0 < n; s0 += chunk, slot = (slot + 1) % SpartCtx::kSlots) {
+      const int64_t m = (n - s0 < chunk) ? (n - s0) : chunk;
+      cudaStream_t st = ctx->streams[slot];
+      int rc2 = unstage(slot);      // the slot's previous chunk (already done unless the CPU is ahead)
+      if (rc2) return rc2;
+      // parameter rows: ld apart on the host, m apart in the slot; a broadcast row moves one element
+      const char* src = pin;
+      size_t src_pitch = (size_t)ld * elt;
+      size_t src_off = (size_t)s0 * elt;
+      if (stage_in) {
+        char* stg = (char*)ctx->stage_in[slot];
+        ctx->pool->parallel_for(P_COUNT, [&](int r) {
+          const bool bc = (broadcast_rows >> r) & 1u;
+          memcpy(stg + (size_t)r * m * elt, pin + (size_t)r * ld * elt + (bc ? 0 : (size_t)s0 * elt),
+                 bc ? elt : (size_t)m * elt);
+        });
+        src = stg;
+        src_pitch = (size_t)m * elt;
+        src_off = 0;
+      }
+      for (int r0 = 0; r0 < P_COUNT;) {     // runs of rows of the same kind become one 2-D copy
+        const bool bc = (broadcast_rows >> r0) & 1u;
+        int r1 = r0 + 1;
+        while (r1 < P_COUNT && (((broadcast_rows >> r1) & 1u) != 0) == bc) ++r1;
+        const size_t off = (bc && !stage_in) ? 0 : src_off;
+        CUDA_TRY(cudaMemcpy2DAsync((char*)ctx->slot_params[slot] + (size_t)r0 * m * elt, (size_t)m * elt,
+                                   src + (size_t)r0 * src_pitch + off, src_pitch, bc ? elt : (size_t)m * elt,
+                                   r1 - r0, cudaMemcpyHostToDevice, st));
+        r0 = r1;
+      }
+      rc2 = spart_forward_bands(ctx, sensor, ctx->slot_params[slot], m, m, broadcast_rows, precision, flags,
+                                ctx->slot_rec[slot], ctx->slot_out[slot], st);
+      if (rc2) return rc2;
+      const size_t main_bytes = (size_t)m * nb * nout * elt;
+      if (stage_out) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->stage_out[slot], ctx->slot_out[slot], main_bytes + (compact ? m * elt : 0),
+                                 cudaMemcpyDeviceToHost, st));
+      } else {
+        CUDA_TRY(cudaMemcpyAsync(pout + (size_t)s0 * nb * nout * elt, ctx->slot_out[slot], main_bytes,
+                                 cudaMemcpyDeviceToHost, st));
+        if (compact)
+          CUDA_TRY(cudaMemcpyAsync(pets + (size_t)s0 * elt, (char*)ctx->slot_out[slot] + main_bytes, (size_t)m * elt,
+                                   cudaMemcpyDeviceToHost, st));
+      }
+      if (stage_in || stage_out) {
+        CUDA_TRY(cudaEventRecord(ctx->slot_done[slot], st));
+        pend[slot].s0 = s0;
+        pend[slot].m = m;
+        pend[slot].live = true;
+        if (stage_out && prev >= 0) {   // copy the previous chunk out while this one is on the GPU
+          rc2 = unstage(prev);
+          if (rc2) return rc2;
+        }
+        prev = slot;
+      }
+    }
+    for (int i = 0; i < SpartCtx::kSlots; ++i) {
+      const int rc2 = unstage(i);
+      if (rc2) return rc2;
+    }
+    return SPART_OK;
+  };
+  rc = run();
+  // on success and on failure alike: nothing of this call may still be in flight (the slot streams
+  // write into the caller's memory) when it returns
+  char keep[sizeof(g_err)];
+  memcpy(keep, g_err, sizeof(keep));
+  for (int i = 0; i < SpartCtx::kSlots; ++i) {
+    const cudaError_t e = cudaStreamSynchronize(ctx->streams[i]);
+    if (e != cudaSuccess && rc == SPART_OK) {
+      snprintf(keep, sizeof(keep), "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+      rc = (int)e;
+    }
   }
-  for (int i = 0; i < SpartCtx::kSlots; ++i) CUDA_TRY(cudaStreamSynchronize(ctx->streams[i]));
-  return SPART_OK;
+  if (rc) memcpy(g_err, keep, sizeof(keep));
+  return rc;
 }
 
 int spart_measure_peaks(int32_t device, double* fp64_tflops, double* fp32_tflops) {
   if (!fp64_tflops || !fp32_tflops) return fail(SPART_EINVAL, "spart_measure_peaks: null argument%s");
-  if (spart_device_count() <= 0) return fail(SPART_ENODEV, "spart_measure_peaks: no CUDA device%s");
-  CUDA_TRY(cudaSetDevice(device));
+  const int ndev = spart_device_count();
+  if (ndev <= 0) return fail(SPART_ENODEV, "spart_measure_peaks: no CUDA device%s");
+  if (device < 0 || device >= ndev) return fail(SPART_EINVAL, "spart_measure_peaks: device index out of range%s");
+  GUARD_DEVICE(device);
   int sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
   int rc = time_fma<double>(sm, fp64_tflops);

@@ -5,19 +5,24 @@ CUDA device, every compute entry point raises.  Build with `python __graft_entry
 (or `python spart-python_b200/build.py`).
 """
 import ctypes
-from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int32, c_int64, c_size_t, c_uint32, c_void_p
 from pathlib import Path
 
 import os
 
 # SPART_B200_LIB lets kernel-tuning scripts load an alternative build of the same library
 LIB_PATH = Path(os.environ.get("SPART_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libspart_b200.so")
-ABI_VERSION = 4
-FLAG_UNIFORM_GEOMETRY = 1
+ABI_VERSION = 5
 FLAG_SOIL_SPECTRUM = 2
 FLAG_SRF_BANDS = 4
 FLAG_REUSE_RECORD = 8
+FLAG_F32_IO = 16
+FLAG_COMPACT_OUT = 32
 NKERNELS = 3
+NPAR = 27
+# rows 19..21 (sun zenith, observer zenith, relative azimuth) as broadcast rows = one geometry for
+# the whole batch by construction; the library then folds it once per thread block
+GEOMETRY_ROWS = (1 << 19) | (1 << 20) | (1 << 21)
 
 FP64 = 64
 FP32 = 32
@@ -25,7 +30,8 @@ FP32 = 32
 EXPORTS = (
     "spart_abi_version", "spart_last_error", "spart_device_count", "spart_create", "spart_destroy",
     "spart_workspace_bytes", "spart_forward_bands", "spart_forward_bands_host", "spart_forward_spectrum",
-    "spart_smac", "spart_sailh", "spart_lut_workspace_bytes", "spart_lut_nearest", "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
+    "spart_smac", "spart_sailh", "spart_lut_workspace_bytes", "spart_lut_nearest", "spart_lut_unpack",
+    "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
 )
 
 
@@ -71,19 +77,20 @@ def load():
     lib.spart_destroy.argtypes = [c_void_p]
     lib.spart_workspace_bytes.argtypes = [c_void_p, c_int64]
     lib.spart_workspace_bytes.restype = c_size_t
-    lib.spart_forward_bands.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p,
-                                        c_void_p, c_void_p]
-    lib.spart_forward_bands_host.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int32, c_int32,
-                                             c_void_p]
-    lib.spart_forward_spectrum.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
-                                           c_void_p]
+    lib.spart_forward_bands.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_uint32, c_int32, c_int32,
+                                        c_void_p, c_void_p, c_void_p]
+    lib.spart_forward_bands_host.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_uint32, c_int32,
+                                             c_int32, c_void_p]
+    lib.spart_forward_spectrum.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_double, c_double,
+                                           c_void_p, c_void_p, c_void_p]
     lib.spart_smac.argtypes = [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
     lib.spart_sailh.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                 c_void_p, c_void_p]
     lib.spart_lut_workspace_bytes.argtypes = [c_int64]
     lib.spart_lut_workspace_bytes.restype = c_size_t
-    lib.spart_lut_nearest.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_void_p]
+    lib.spart_lut_nearest.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.spart_lut_unpack.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]
     lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]
@@ -102,6 +109,21 @@ def check(rc, what):
         raise SpartError(f"{what}: {kind} {rc}: {msg}")
 
 
+def row_mask(rows):
+    """Bit mask of `broadcast_rows` from an int mask or an iterable of row indices (0..26)."""
+    if rows is None:
+        return 0
+    if isinstance(rows, int):
+        mask = rows
+    else:
+        mask = 0
+        for r in rows:
+            mask |= 1 << int(r)
+    if mask < 0 or mask >> NPAR:
+        raise ValueError("broadcast_rows: rows are 0..26")
+    return mask
+
+
 def as_double_ptr(a):
     return a.ctypes.data_as(POINTER(c_double))
 
@@ -110,5 +132,5 @@ def as_int32_ptr(a):
     return a.ctypes.data_as(POINTER(c_int32))
 
 
-__all__ = ["load", "check", "SpartError", "SpartTables", "SpartSensor", "FP64", "FP32", "EXPORTS",
+__all__ = ["load", "check", "SpartError", "SpartTables", "SpartSensor", "FP64", "FP32", "EXPORTS", "row_mask",
            "as_double_ptr", "as_int32_ptr", "byref", "c_void_p", "c_double", "c_int64"]

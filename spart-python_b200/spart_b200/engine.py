@@ -2,9 +2,11 @@
 
 PyTorch is used for device memory, streams and (in distributed.py) NCCL only; all
 arithmetic happens in libspart_b200.so.  A context (immutable device tables) is created
-lazily per sensor and cached.
+lazily per sensor and cached (bounded, least recently used first out).
 """
+import hashlib
 import threading
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -17,6 +19,7 @@ NOUT = 3
 NSPEC = 9
 NWL_S = 2162
 MAX_SAMPLES_PER_CALL = 65535 * 128    # grid.y limit of band_kernel, see spart_forward_bands
+MAX_CONTEXTS = 32                     # cached (sensor, soil spectrum) contexts per engine
 
 _PRECISION = {"fp64": _lib.FP64, 64: _lib.FP64, "fp32": _lib.FP32, 32: _lib.FP32}
 
@@ -24,6 +27,58 @@ _PRECISION = {"fp64": _lib.FP64, 64: _lib.FP64, "fp32": _lib.FP32, 32: _lib.FP32
 def _require_cuda():
     if not torch.cuda.is_available():
         raise _lib.SpartError("spart_b200 needs a CUDA device (B200); there is no CPU fallback")
+
+
+def out_elems(n, nb, compact):
+    """Elements of a result buffer (SPART_OUT_ELEMS of include/spart_b200.h)."""
+    return n * nb * 2 + n if compact else n * nb * NOUT
+
+
+class CompactBands:
+    """Result of a `compact=True` run: `R` [n, nb, 2] = (R_TOC, R_TOA) and `etscale` [n], both views of
+    one flat buffer (SPART_FLAG_COMPACT_OUT), plus the sensor's SRF-convolved extraterrestrial
+    irradiance `conv_ea` [nb].  `L_TOA` is rebuilt bit for bit as the kernels form it:
+    (conv_ea[b] * etscale[s]) * R_TOA[s, b] (SPART.py:252) in the buffer's dtype."""
+
+    def __init__(self, buf, n, nb, conv_ea):
+        self.buf, self.n, self.nb = buf, n, nb
+        self.R = buf[:n * nb * 2].reshape(n, nb, 2)
+        self.etscale = buf[n * nb * 2:n * nb * 2 + n]
+        if isinstance(buf, torch.Tensor):
+            self.conv_ea = torch.as_tensor(np.asarray(conv_ea, dtype=np.float64), device=buf.device).to(buf.dtype)
+        else:
+            self.conv_ea = np.asarray(conv_ea, dtype=np.float64).astype(buf.dtype)
+
+    @property
+    def R_TOC(self):
+        return self.R[..., 0]
+
+    @property
+    def R_TOA(self):
+        return self.R[..., 1]
+
+    @property
+    def L_TOA(self):
+        return (self.conv_ea[None, :] * self.etscale[:, None]) * self.R[..., 1]
+
+    def full(self):
+        """[n, nb, 3] = (R_TOC, R_TOA, L_TOA), identical to a non-compact run."""
+        if isinstance(self.buf, torch.Tensor):
+            return torch.cat([self.R, self.L_TOA[..., None]], dim=2)
+        return np.concatenate([self.R, self.L_TOA[..., None]], axis=2)
+
+
+def _sensor_digest(info):
+    """Content hash of everything the hot path uses of a sensorinfo dict."""
+    h = hashlib.sha1()
+    for k in ("wl_smac", "wl_srf_smac", "p_srf_smac"):
+        a = np.ascontiguousarray(np.asarray(info[k]))
+        h.update(k.encode() + str(a.dtype).encode() + str(a.shape).encode() + a.tobytes())
+    for k in sorted(info["SMAC_coef"]):
+        a = np.ascontiguousarray(np.asarray(info["SMAC_coef"][k]))
+        h.update(k.encode() + str(a.dtype).encode() + a.tobytes())
+    h.update("\x1f".join(str(b) for b in info["band_id_smac"]).encode())
+    return h.hexdigest()
 
 
 class Engine:
@@ -38,25 +93,28 @@ class Engine:
                                    (device.index if isinstance(device, torch.device) else int(device)))
         self._opt = T.load_optical()
         self._lc = T.leaf_soil_constants(self._opt)
-        self._ctx = {}        # key -> (ctx handle, SensorTables, keep-alive arrays)
+        self._ctx = OrderedDict()   # key -> (ctx handle, SensorTables, keep-alive arrays); LRU order
         self._lock = threading.Lock()
 
     # ---- contexts ------------------------------------------------------------------
     def sensor(self, sensor, soil_spectrum=None):
         """(ctx, SensorTables) for a shipped sensor name or a reference-style sensorinfo dict.
-        soil_spectrum: optional user dry-soil reflectance [2001] (SoilParametersFromFile); such a
-        context carries the spectrum as its first soil vector and must be run with
-        SPART_FLAG_SOIL_SPECTRUM."""
-        skey = sensor if isinstance(sensor, str) else ("custom", id(sensor))
+        Custom dicts are keyed by the content of every array the hot path uses (so an edited dict
+        is a new sensor).  soil_spectrum: optional user dry-soil reflectance [2001]
+        (SoilParametersFromFile); such a context carries the spectrum as its first soil vector and
+        must be run with SPART_FLAG_SOIL_SPECTRUM.  At most MAX_CONTEXTS contexts are kept; the least
+        recently used one is destroyed (its device tables are freed) when a new one is needed."""
+        skey = sensor if isinstance(sensor, str) else ("custom", _sensor_digest(sensor))
         soil = None
         if soil_spectrum is not None:
             soil = np.ascontiguousarray(np.asarray(soil_spectrum, dtype=np.float64).reshape(-1))
             if soil.shape[0] != T.NWL:
                 raise ValueError("soil_spectrum must have 2001 values (400..2400 nm)")
-        key = (skey, None if soil is None else soil.tobytes())
+        key = (skey, None if soil is None else hashlib.sha1(soil.tobytes()).hexdigest())
         with self._lock:
             hit = self._ctx.get(key)
             if hit is not None:
+                self._ctx.move_to_end(key)
                 return hit[0], hit[1]
             info = T.load_sensor_info(sensor) if isinstance(sensor, str) else sensor
             st = T.build_sensor(sensor if isinstance(sensor, str) else "custom", info, self._opt)
@@ -74,7 +132,10 @@ class Engine:
             handle = _lib.c_void_p()
             _lib.check(self.lib.spart_create(_lib.byref(tabs), _lib.byref(cs), 1, self.device.index,
                                              _lib.byref(handle)), "spart_create")
-            self._ctx[key] = (handle, st, (smac, sensor, lc))
+            while len(self._ctx) >= MAX_CONTEXTS:
+                _, (old, _, _) = self._ctx.popitem(last=False)
+                self.lib.spart_destroy(old)
+            self._ctx[key] = (handle, st, (smac, lc))
             return handle, st
 
     def close(self):
@@ -90,78 +151,118 @@ class Engine:
             pass
 
     # ---- device path ---------------------------------------------------------------
-    def _prep(self, params):
-        if not (isinstance(params, torch.Tensor) and params.is_cuda and params.dtype == torch.float64
-                and params.dim() == 2 and params.shape[0] == NPAR
-                and (params.shape[1] <= 1 or params.stride(1) == 1)):
-            raise ValueError("params must be a CUDA float64 tensor [27, n] with contiguous rows")
+    def _prep(self, params, allow_f32=False):
+        ok = (isinstance(params, torch.Tensor) and params.is_cuda and params.dim() == 2 and params.shape[0] == NPAR
+              and (params.shape[1] <= 1 or params.stride(1) == 1)
+              and (params.dtype == torch.float64 or (allow_f32 and params.dtype == torch.float32)))
+        if not ok:
+            raise ValueError("params must be a CUDA float64 tensor [27, n] with contiguous rows"
+                             " (float32 is accepted with precision='fp32')")
         if params.device != self.device:
             raise ValueError(f"params on {params.device}, engine on {self.device}")
         return params, params.shape[1], (params.stride(0) if params.shape[1] > 1 else max(params.shape[1], 1))
 
-    def forward_bands(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
-                      soil_spectrum=None, band_mode="interp"):
-        """params: CUDA float64 [27, n] -> CUDA float64 [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
-        Asynchronous on the current torch stream.  uniform_geometry=True asserts that the three
-        angle rows are constant over the batch (SPART_FLAG_UNIFORM_GEOMETRY).  soil_spectrum: dry
-        soil reflectance [2001] used instead of the B/lat/lon soil vectors.  band_mode: "interp"
-        (the reference: np.interp at the band centre) or "srf" (SRF-weighted band means)."""
+    def _geometry_mask(self, params, n, mask, uniform_geometry):
+        """uniform_geometry=True is checked, not trusted: unless the three angle rows already are
+        broadcast rows they must be constant over the batch (one small reduction and a
+        synchronisation); they are then passed as broadcast rows, which is what selects the
+        folded-geometry kernels."""
+        if not uniform_geometry or (mask & _lib.GEOMETRY_ROWS) == _lib.GEOMETRY_ROWS or n == 0:
+            return mask
+        ang = params[19:22, :n]
+        same = bool((ang == ang[:, :1]).all().item()) if isinstance(params, torch.Tensor) else bool(
+            (ang == ang[:, :1]).all())
+        if not same:
+            raise _lib.SpartError("uniform_geometry=True, but the sun / observer angle rows 19..21 vary over the batch")
+        return mask | _lib.GEOMETRY_ROWS
+
+    @staticmethod
+    def _flags(soil_spectrum, band_mode, f32_io=False, compact=False, reuse=False):
         if band_mode not in ("interp", "srf"):
             raise ValueError("band_mode must be 'interp' or 'srf'")
-        handle, st = self.sensor(sensor, soil_spectrum)
-        params, n, ld = self._prep(params)
-        if out is None:
-            out = torch.empty((n, st.n_bands, NOUT), dtype=torch.float64, device=self.device)
-        elif not (out.is_cuda and out.dtype == torch.float64 and out.is_contiguous()
-                  and tuple(out.shape) == (n, st.n_bands, NOUT)):
-            raise ValueError("out must be a contiguous CUDA float64 tensor [n, nb, 3]")
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        return ((_lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0)
+                | (_lib.FLAG_SRF_BANDS if band_mode == "srf" else 0)
+                | (_lib.FLAG_F32_IO if f32_io else 0) | (_lib.FLAG_COMPACT_OUT if compact else 0)
+                | (_lib.FLAG_REUSE_RECORD if reuse else 0))
+
+    def workspace(self, n):
+        """Device scratch for a batch of n samples (spart_workspace_bytes)."""
+        return torch.empty(max(self.lib.spart_workspace_bytes(None, n) // 8, 1), dtype=torch.float64, device=self.device)
+
+    def forward_bands(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
+                      soil_spectrum=None, band_mode="interp", broadcast_rows=0, compact=False,
+                      reuse_record=False, workspace=None):
+        """params: CUDA float64 [27, n] -> CUDA float64 [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
+        Asynchronous on the current torch stream.
+
+        broadcast_rows: bit mask / iterable of rows that are constant over the batch (only their
+        element 0 is read).  uniform_geometry=True: the three angle rows are verified to be constant
+        and passed as broadcast rows (raises SpartError otherwise).  soil_spectrum: dry soil
+        reflectance [2001] used instead of the B/lat/lon soil vectors.  band_mode: "interp" (the
+        reference: np.interp at the band centre) or "srf" (SRF-weighted band means).
+        precision="fp32" with float32 params: float32 in, float32 out (SPART_FLAG_F32_IO).
+        compact=True: returns a CompactBands (R_TOC, R_TOA + etscale; two thirds of the bytes).
+        `out`: result buffer to fill ([n, nb, 3], or flat with out_elems(n, nb, True) elements when
+        compact)."""
         prec = _PRECISION[precision]
-        flags = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
-            _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0) | (
-            _lib.FLAG_SRF_BANDS if band_mode == "srf" else 0)
-        for s0 in range(0, n, MAX_SAMPLES_PER_CALL):
-            m = min(MAX_SAMPLES_PER_CALL, n - s0)
-            ws = torch.empty(self.lib.spart_workspace_bytes(handle, m) // 8, dtype=torch.float64, device=self.device)
-            _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr() + 8 * s0, m, ld, prec, flags,
-                                                    ws.data_ptr(), out.data_ptr() + 8 * s0 * st.n_bands * NOUT,
-                                                    stream), "spart_forward_bands")
-        return out
+        handle, st = self.sensor(sensor, soil_spectrum)
+        params, n, ld = self._prep(params, allow_f32=(prec == _lib.FP32))
+        f32_io = params.dtype == torch.float32
+        mask = self._geometry_mask(params, n, _lib.row_mask(broadcast_rows), uniform_geometry)
+        flags = self._flags(soil_spectrum, band_mode, f32_io, compact, reuse_record)
+        nb = st.n_bands
+        elems = out_elems(n, nb, compact)
+        if out is None:
+            out = torch.empty(elems if compact else (n, nb, NOUT), dtype=params.dtype, device=self.device)
+        elif not (out.is_cuda and out.dtype == params.dtype and out.is_contiguous() and out.numel() == elems
+                  and (compact or tuple(out.shape) == (n, nb, NOUT))):
+            raise ValueError("out must be a contiguous CUDA tensor of the params' dtype: [n, nb, 3], or flat with"
+                             " n*nb*2 + n elements when compact")
+        if n > MAX_SAMPLES_PER_CALL and (compact or reuse_record):
+            raise ValueError(f"compact / reuse_record runs handle at most {MAX_SAMPLES_PER_CALL} samples per call")
+        esz = params.element_size()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            for s0 in range(0, n, MAX_SAMPLES_PER_CALL):
+                m = min(MAX_SAMPLES_PER_CALL, n - s0)
+                ws = workspace if (workspace is not None and s0 == 0 and m == n) else self.workspace(m)
+                _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr() + esz * s0, m, ld, mask, prec, flags,
+                                                        ws.data_ptr(), out.data_ptr() + esz * s0 * nb * NOUT,
+                                                        stream), "spart_forward_bands")
+        return CompactBands(out, n, nb, st.conv_ea) if compact else out
 
     def forward_bands_multi(self, params, sensors, outs=None, precision="fp64", uniform_geometry=False,
-                            soil_spectrum=None, band_mode="interp"):
+                            soil_spectrum=None, band_mode="interp", broadcast_rows=0, compact=False):
         """One batch evaluated for several sensors: the sensor-independent per-sample kernels run
         once and every further sensor only runs the band kernel (SPART_FLAG_REUSE_RECORD).
-        Returns a list of CUDA float64 [n, nb_i, 3] tensors."""
-        params, n, ld = self._prep(params)
+        Returns a list of results as forward_bands would."""
+        n = params.shape[1]
         if n > MAX_SAMPLES_PER_CALL:
             raise ValueError(f"forward_bands_multi handles at most {MAX_SAMPLES_PER_CALL} samples per call")
-        ctxs = [self.sensor(s, soil_spectrum) for s in sensors]
-        if outs is None:
-            outs = [torch.empty((n, st.n_bands, NOUT), dtype=torch.float64, device=self.device) for _, st in ctxs]
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        base = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
-            _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0) | (
-            _lib.FLAG_SRF_BANDS if band_mode == "srf" else 0)
-        ws = torch.empty(self.lib.spart_workspace_bytes(ctxs[0][0], n) // 8, dtype=torch.float64, device=self.device)
-        for i, ((handle, st), out) in enumerate(zip(ctxs, outs)):
-            flags = base | (_lib.FLAG_REUSE_RECORD if i > 0 else 0)
-            _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr(), n, ld, _PRECISION[precision], flags,
-                                                    ws.data_ptr(), out.data_ptr(), stream), "spart_forward_bands")
-        return outs
+        mask = self._geometry_mask(params, n, _lib.row_mask(broadcast_rows), uniform_geometry)
+        ws = self.workspace(n)
+        res = []
+        for i, s in enumerate(sensors):
+            res.append(self.forward_bands(params, s, out=None if outs is None else outs[i], precision=precision,
+                                          soil_spectrum=soil_spectrum, band_mode=band_mode, broadcast_rows=mask,
+                                          compact=compact, reuse_record=i > 0, workspace=ws))
+        return res
 
-    def forward_spectrum(self, params, out=None, soil_spectrum=None):
+    def forward_spectrum(self, params, out=None, soil_spectrum=None, rho_thermal=0.01, tau_thermal=0.01):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, 9, 2162]: leaf refl, leaf tran,
-        kChlrel, soil refl, soil refl dry, rso, rdo, rsd, rdd."""
+        kChlrel, soil refl, soil refl dry, rso, rdo, rsd, rdd.  rho_thermal / tau_thermal: leaf
+        reflectance / transmittance beyond 2400 nm (LeafBiology.rho_thermal / tau_thermal)."""
         handle, _ = self.sensor("Sentinel2A-MSI", soil_spectrum)   # any context carries the wavelength tables
         params, n, ld = self._prep(params)
         if out is None:
             out = torch.empty((n, NSPEC, NWL_S), dtype=torch.float64, device=self.device)
-        ws = torch.empty(self.lib.spart_workspace_bytes(handle, n) // 8, dtype=torch.float64, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self.workspace(n)
         flags = _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0
-        _lib.check(self.lib.spart_forward_spectrum(handle, params.data_ptr(), n, ld, flags, ws.data_ptr(),
-                                                   out.data_ptr(), stream), "spart_forward_spectrum")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.spart_forward_spectrum(handle, params.data_ptr(), n, ld, flags, float(rho_thermal),
+                                                       float(tau_thermal), ws.data_ptr(), out.data_ptr(), stream),
+                       "spart_forward_spectrum")
         return out
 
     def smac(self, params, sensor, out=None):
@@ -171,10 +272,11 @@ class Engine:
         params, n, ld = self._prep(params)
         if out is None:
             out = torch.empty((n, 9, st.n_bands), dtype=torch.float64, device=self.device)
-        ws = torch.empty(self.lib.spart_workspace_bytes(handle, n) // 8, dtype=torch.float64, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.spart_smac(handle, 0, params.data_ptr(), n, ld, ws.data_ptr(), out.data_ptr(), stream),
-                   "spart_smac")
+        ws = self.workspace(n)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.spart_smac(handle, 0, params.data_ptr(), n, ld, ws.data_ptr(), out.data_ptr(), stream),
+                       "spart_smac")
         return out
 
     def sailh(self, params, soil_refl, leaf_refl, leaf_tran, out=None):
@@ -193,55 +295,61 @@ class Engine:
                                    "(CUDA float64, all three spectra [2162] or all [n, 2162])")
         if out is None:
             out = torch.empty((n, 4, NWL_S), dtype=torch.float64, device=self.device)
-        ws = torch.empty(self.lib.spart_workspace_bytes(handle, n) // 8, dtype=torch.float64, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.spart_sailh(handle, params.data_ptr(), n, ld, soil_refl.data_ptr(), leaf_refl.data_ptr(),
-                                        leaf_tran.data_ptr(), 0 if shared else NWL_S, ws.data_ptr(), out.data_ptr(),
-                                        stream), "spart_sailh")
+        ws = self.workspace(n)
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.spart_sailh(handle, params.data_ptr(), n, ld, soil_refl.data_ptr(),
+                                            leaf_refl.data_ptr(), leaf_tran.data_ptr(), 0 if shared else NWL_S,
+                                            ws.data_ptr(), out.data_ptr(), stream), "spart_sailh")
         return out
 
     def leafangles(self, ab):
         """[n, 2] (LIDFa, LIDFb) host array -> [n, 13] lidf host array."""
         ab = np.ascontiguousarray(np.asarray(ab, dtype=np.float64).reshape(-1, 2).T)
         n = ab.shape[1]
-        d = torch.from_numpy(ab).to(self.device)
-        out = torch.empty((n, 13), dtype=torch.float64, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.lib.spart_leafangles(d.data_ptr(), n, n, out.data_ptr(), stream), "spart_leafangles")
-        return out.cpu().numpy()
+        with torch.cuda.device(self.device):
+            d = torch.from_numpy(ab).to(self.device)
+            out = torch.empty((n, 13), dtype=torch.float64, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self.lib.spart_leafangles(d.data_ptr(), n, n, out.data_ptr(), stream), "spart_leafangles")
+            return out.cpu().numpy()
 
     # ---- host path -----------------------------------------------------------------
     def forward_bands_host(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
-                           soil_spectrum=None, band_mode="interp"):
-        """params: host float64 [27, n] (NumPy array or CPU tensor, ideally pinned) ->
-        host float64 [n, nb, 3].  H2D, kernels and D2H are pipelined inside the C library."""
+                           soil_spectrum=None, band_mode="interp", broadcast_rows=0, compact=False):
+        """params: host float64 [27, n] (NumPy array or CPU tensor; float32 with precision="fp32") ->
+        host array [n, nb, 3] of the same dtype (CompactBands when compact).  H2D, kernels and D2H are
+        pipelined inside the C library; pinned memory is DMA'd directly, pageable memory is staged
+        by the library's copy threads.  Other arguments as forward_bands."""
+        prec = _PRECISION[precision]
         handle, st = self.sensor(sensor, soil_spectrum)
         p = params.numpy() if isinstance(params, torch.Tensor) else np.asarray(params)
-        if p.dtype != np.float64 or p.ndim != 2 or p.shape[0] != NPAR or (p.shape[1] > 1 and p.strides[1] != 8):
-            raise ValueError("params must be a host float64 array [27, n] with contiguous rows")
-        n = p.shape[1]
-        ld = p.strides[0] // 8 if n > 1 else max(n, 1)
+        okdt = p.dtype == np.float64 or (p.dtype == np.float32 and prec == _lib.FP32)
+        if not okdt or p.ndim != 2 or p.shape[0] != NPAR or (p.shape[1] > 1 and p.strides[1] != p.itemsize):
+            raise ValueError("params must be a host float64 array [27, n] with contiguous rows"
+                             " (float32 is accepted with precision='fp32')")
+        n, nb = p.shape[1], st.n_bands
+        ld = p.strides[0] // p.itemsize if n > 1 else max(n, 1)
+        mask = self._geometry_mask(p, n, _lib.row_mask(broadcast_rows), uniform_geometry)
+        flags = self._flags(soil_spectrum, band_mode, p.dtype == np.float32, compact)
+        elems = out_elems(n, nb, compact)
         if out is None:
-            out = np.empty((n, st.n_bands, NOUT), dtype=np.float64)
+            out = np.empty(elems if compact else (n, nb, NOUT), dtype=p.dtype)
         o = out.numpy() if isinstance(out, torch.Tensor) else out
-        if o.dtype != np.float64 or not o.flags.c_contiguous or o.shape != (n, st.n_bands, NOUT):
-            raise ValueError("out must be a C-contiguous host float64 array [n, nb, 3]")
-        with torch.cuda.device(self.device):
-            if band_mode not in ("interp", "srf"):
-                raise ValueError("band_mode must be 'interp' or 'srf'")
-            flags = (_lib.FLAG_UNIFORM_GEOMETRY if uniform_geometry else 0) | (
-                _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0) | (
-                _lib.FLAG_SRF_BANDS if band_mode == "srf" else 0)
-            _lib.check(self.lib.spart_forward_bands_host(handle, 0, p.ctypes.data, n, ld, _PRECISION[precision],
-                                                         flags, o.ctypes.data), "spart_forward_bands_host")
-        return out
+        if o.dtype != p.dtype or not o.flags.c_contiguous or o.size != elems or not (
+                compact or o.shape == (n, nb, NOUT)):
+            raise ValueError("out must be a C-contiguous host array of the params' dtype: [n, nb, 3], or flat with"
+                             " n*nb*2 + n elements when compact")
+        _lib.check(self.lib.spart_forward_bands_host(handle, 0, p.ctypes.data, n, ld, mask, prec, flags,
+                                                     o.ctypes.data), "spart_forward_bands_host")
+        return CompactBands(out, n, nb, st.conv_ea) if compact else out
 
     def profile_enable(self, sensor, on=True):
         handle, _ = self.sensor(sensor)
         _lib.check(self.lib.spart_profile_enable(handle, 1 if on else 0), "spart_profile_enable")
 
     def profile_read(self, sensor):
-        """Summed CUDA-event durations of the two kernels since the last read:
+        """Summed CUDA-event durations of the three kernels since the last read:
         {'lidf_ms', 'geometry_ms', 'band_ms', 'calls'}."""
         handle, _ = self.sensor(sensor)
         ms = (_lib.c_double * _lib.NKERNELS)()

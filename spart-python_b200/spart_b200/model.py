@@ -14,7 +14,7 @@ import pandas as pd
 import torch
 
 from . import tables as T
-from .engine import default_engine
+from .engine import _sensor_digest, default_engine
 from .params import pack_params
 
 
@@ -55,6 +55,8 @@ class SPART:
         self.spectral = SpectralBands()
         self.sensorinfo = load_sensor_info(sensor)       # FileNotFoundError for unknown sensors
         self._loaded_sensor = sensor
+        self._shipped_info = self.sensorinfo
+        self._shipped_digest = _sensor_digest(self.sensorinfo)
         self._spec = None
 
     def _params(self):
@@ -67,11 +69,13 @@ class SPART:
 
     def _sensor_key(self):
         # like the reference, a changed `sensor` attribute does not reload sensorinfo; a user
-        # may however assign a custom sensorinfo dict (SPART.py:95 is a plain attribute)
-        shipped = T.load_sensor_info(self._loaded_sensor) if isinstance(self._loaded_sensor, str) else None
-        same = shipped is not None and self.sensorinfo.keys() == shipped.keys() and all(
-            np.array_equal(np.asarray(self.sensorinfo[k]), np.asarray(shipped[k]), equal_nan=True)
-            for k in ("wl_smac", "wl_srf_smac", "p_srf_smac"))
+        # may however assign or edit the sensorinfo dict (SPART.py:95 is a plain attribute): every
+        # array the hot path uses is compared with the shipped table, an edited dict is a custom sensor
+        # (the engine keys those by content)
+        if self.sensorinfo is self._shipped_info:
+            same = self._shipped_digest == _sensor_digest(self.sensorinfo)
+        else:
+            same = False
         return self._loaded_sensor if same else self.sensorinfo
 
     def run(self, debug=False):
@@ -83,12 +87,13 @@ class SPART:
                   "therefore set to zero (Cdm = PROT + CBC)")
         key = self._sensor_key()
         p = self._params()
-        out = eng.forward_bands_host(p, key, soil_spectrum=self._soil_spectrum())[0]            # [nb, 3]
+        soil = self._soil_spectrum()
+        out = eng.forward_bands_host(p, key, soil_spectrum=soil)[0]            # [nb, 3]
         self.R_TOC = out[:, 0][None, :].copy()
         self.R_TOA = out[:, 1][None, :].copy()
         self.L_TOA = out[:, 2][None, :].copy()
         self._spec = None
-        _, st = eng.sensor(key)
+        _, st = eng.sensor(key, soil)          # the context that just ran (cached)
         table = pd.DataFrame(zip(st.band_id, self.L_TOA[0], self.R_TOA[0], self.R_TOC[0]),
                              index=st.wl_smac, columns=["Band", "L_TOA", "R_TOA", "R_TOC"])
         if debug:
@@ -100,7 +105,9 @@ class SPART:
         if self._spec is None:
             eng = default_engine()
             p = torch.from_numpy(self._params()).to(eng.device)
-            self._spec = eng.forward_spectrum(p, soil_spectrum=self._soil_spectrum())[0].cpu().numpy()     # [9, 2162]
+            self._spec = eng.forward_spectrum(p, soil_spectrum=self._soil_spectrum(),
+                                              rho_thermal=getattr(self.leafbio, "rho_thermal", 0.01),
+                                              tau_thermal=getattr(self.leafbio, "tau_thermal", 0.01))[0].cpu().numpy()
         return self._spec
 
     @property

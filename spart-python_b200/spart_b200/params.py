@@ -124,6 +124,13 @@ class CanopyStructure:
             self._lidf = default_engine().leafangles(np.array([[self.LIDFa, self.LIDFb]], dtype=np.float64))[0][:, None]
         return self._lidf
 
+    @lidf.setter
+    def lidf(self, value):
+        # the reference would use an assigned distribution as is (sailh.py:93-97 read canopy.lidf);
+        # the GPU path always derives it from LIDFa / LIDFb, so an assignment must not pass silently
+        raise NotImplementedError("a user-assigned lidf is not supported: the GPU path derives the leaf "
+                                  "inclination distribution from LIDFa / LIDFb (set those instead)")
+
     def as_row(self):
         return [self.LAI, self.LIDFa, self.LIDFb, self.q]
 

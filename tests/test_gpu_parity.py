@@ -395,6 +395,19 @@ def test_srf_band_mode(env, sensor, cfg):
         sb.run_batch_params(dev, sensor, band_mode="srf", precision="fp32")
 
 
+@pytest.mark.parametrize("name", ["srf_Sentinel2A", "srf_LANDSAT8", "srf_TerraAqua"])
+def test_srf_band_mode_vs_reference_golden(env, name):
+    """SRF band mode against goldens recorded from the reference itself: its
+    calculate_spectral_convolution (SPART.py:358-396) applied to its canopyopt, then its own atmopt
+    and TOC->TOA algebra (tools/make_golden.py::run_srf)."""
+    torch, sb, _ = env
+    g = load_golden(f"{name}.npz")
+    dev = torch.from_numpy(np.ascontiguousarray(g["params"].T)).cuda()
+    got = sb.run_batch_params(dev, str(g["sensor"]), band_mode="srf").cpu().numpy()
+    assert relerr(got, g["O2"]) < RTOL64
+    assert relerr(got, g["O1"]) < 5e-8
+
+
 def test_multi_sensor_shares_the_per_sample_work(env):
     """Config 5 of BASELINE.json (Sentinel-2A + -2B on one batch): the second sensor reuses the
     per-sample record (SPART_FLAG_REUSE_RECORD) and must give exactly the single-sensor result."""

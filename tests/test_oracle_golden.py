@@ -116,3 +116,23 @@ def test_closest_index_semantics():
     wl = np.array([[350.0, 400.5], [np.nan, 2400.49], [2500.0, 1000.0]])
     idx = so.closest_index(wl, wl_hi)
     assert idx.tolist() == [[0, 0], [0, 2000], [2000, 600]]
+
+
+def test_oracle_bare_soil_rows(optical):
+    """LAI = 0 and LAI -> 0 rows recorded from the unmodified reference (sailh.py:112-114)."""
+    g = load_golden("edge_lai0.npz")
+    got = so.spart_bands(g["params"], str(g["sensor"]), optical)
+    assert np.isfinite(g["O1"]).all()
+    assert relerr(got, g["O2"]) < 1e-12
+    assert relerr(got, g["O1"]) < 5e-8
+
+
+@pytest.mark.parametrize("name", ["srf_Sentinel2A", "srf_LANDSAT8", "srf_TerraAqua"])
+def test_oracle_srf_band_mode_is_the_references_convolution(name, optical):
+    """band_mode="srf" against the reference's own calculate_spectral_convolution (SPART.py:358-396)
+    applied to the canopyopt of a reference run, followed by the reference's atmopt and TOC->TOA algebra
+    (recorded by tools/make_golden.py::run_srf)."""
+    g = load_golden(f"{name}.npz")
+    got = so.spart_bands(g["params"], str(g["sensor"]), optical, band_mode="srf")
+    assert relerr(got, g["O2"]) < 1e-12
+    assert relerr(got, g["O1"]) < 5e-8

@@ -124,6 +124,34 @@ def run_sailh(task):
     return np.stack([r.rso[:, 0], r.rdo[:, 0], r.rsd[:, 0], r.rdd[:, 0]]), canopy.lidf[:, 0]
 
 
+def run_srf(task):
+    """SRF band mode golden from the reference's own functions: calculate_spectral_convolution
+    (SPART.py:358-396) applied to the four canopyopt spectra of a reference run, then the reference's SMAC
+    output and TOC->TOA algebra (SPART.py:235-252) as they stand after run()."""
+    import contextlib
+    import io
+    p, sensor, o2 = task
+    SPART = _ref_modules(o2)
+    from SPART.SPART import calculate_spectral_convolution
+    soil, leaf, canopy, atm, angles = _objects(SPART, p)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sp = SPART.SPART(soil, leaf, canopy, atm, angles, sensor, int(p[26]))
+        df = sp.run()
+    wl = sp.ETpar["wl_Ea"] if hasattr(sp, "ETpar") else np.arange(400, 2401)[:, None]
+    rv = {k: calculate_spectral_convolution(wl, getattr(sp.canopyopt, k)[:2001], sp.sensorinfo)
+          for k in ("rso", "rdo", "rdd", "rsd")}
+    a = sp.atmopt
+    La = sp._La                        # SRF-convolved ET radiance of this sample, SPART.py:183-185
+    rtoa0 = a.Ra_so + a.Ta_ss * rv["rso"] * a.Ta_oo
+    rtoa1 = ((a.Ta_sd * rv["rdo"] + a.Ta_ss * rv["rsd"] * a.Ra_dd * rv["rdo"]) * a.Ta_oo) / (1 - rv["rdd"] * a.Ra_dd)
+    rtoa2 = (a.Ta_ss * rv["rsd"] + a.Ta_sd * rv["rdd"]) * a.Ta_do / (1 - rv["rdd"] * a.Ra_dd)
+    R_TOC = (a.Ta_ss * rv["rso"] + a.Ta_sd * rv["rdo"]) / (a.Ta_ss + a.Ta_sd)
+    R_TOA = a.Tg * (rtoa0 + rtoa1 + rtoa2)
+    band = np.stack([rv["rso"], rv["rdo"], rv["rsd"], rv["rdd"]], axis=1)
+    L_TOA = La * R_TOA
+    return np.stack([R_TOC[0], R_TOA[0], L_TOA[0]], axis=1), band
+
+
 def conftest_defaults():
     """tests/conftest.py:90-112 defaults, DOY 100 (tests/e2e/test_SPART.py:30-39)."""
     p = np.zeros(27)
@@ -177,6 +205,35 @@ def main():
             np.savez_compressed(GOLD / f"soilfile_{sensor.split('-')[0]}.npz", params=P, rdry=rdry,
                                 sensor=np.array(sensor), O1=o1, O2=o2)
         print("soilfile done", flush=True)
+        if args.only:
+            pool.close()
+            return
+
+    # 7. bare soil (LAI = 0 and LAI -> 0) with narrow and wide hot spots: sailh.py:112-114 guards LAI > 0
+    if args.only in (None, "edge"):
+        P = so.synthetic_params(12, 3, seed=62)
+        P[:, so.LAI] = [0, 0, 0, 0, 0, 0, 1e-9, 1e-6, 1e-4, 1e-3, 0, 0]
+        P[:, so.HOT_Q] = [0.01, 0.05, 0.001, 0.2, 0.01, 0.05, 0.01, 0.05, 0.01, 0.05, 0.01, 0.05]
+        P[4:6, so.SZA], P[4:6, so.VZA], P[4:6, so.RAA] = 40.0, 0.0, 0.0
+        P[10:12, so.VZA], P[10:12, so.RAA] = P[10:12, so.SZA], 0.0        # bare soil in the exact hot spot
+        r = run_batch(P, "LANDSAT8-OLI")
+        np.savez_compressed(GOLD / "edge_lai0.npz", params=P, sensor=np.array("LANDSAT8-OLI"), O1=r["O1"], O2=r["O2"])
+        print("edge done", flush=True)
+        if args.only:
+            pool.close()
+            return
+
+    # 8. SRF band mode from the reference's own calculate_spectral_convolution on its canopyopt
+    if args.only in (None, "srf"):
+        for sensor, cfg in (("Sentinel2A-MSI", 2), ("LANDSAT8-OLI", 3), ("TerraAqua-MODIS", 3)):
+            P = so.synthetic_params(12, cfg, seed=63)
+            res = {}
+            for tag, o2 in (("O1", False), ("O2", True)):
+                r = pool.map(run_srf, [(p, sensor, o2) for p in P], chunksize=1)
+                res[tag] = np.stack([x[0] for x in r])
+                res[tag + ".canopy_bands"] = np.stack([x[1] for x in r])
+            np.savez_compressed(GOLD / f"srf_{sensor.split('-')[0]}.npz", params=P, sensor=np.array(sensor), **res)
+        print("srf done", flush=True)
         if args.only:
             pool.close()
             return
