@@ -512,6 +512,9 @@ __device__ __forceinline__ LeafPar load_leaf(const Params& P, int64_t s) {
   return L;
 }
 
+__device__ __forceinline__ void leaf_from_tau(double tau, double t_alph, double t12, double t21, double N,
+                                              double& refl, double& tran);
+
 // lc: the SPART_NLC constants of this wavelength.  Returns refl, tran (and kChlrel).
 template <bool kWantKchl>
 __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* lc, const TauTable* tab,
@@ -525,7 +528,14 @@ __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* l
     tau = plate_tau(Kall, tab);
     if (kWantKchl) kchl = L.Cab * lc[LC_KAB] / (Kall * L.N);
   }
-  const double t_alph = lc[LC_TALPH], t12 = lc[LC_T12], t21 = lc[LC_T21];
+  leaf_from_tau(tau, lc[LC_TALPH], lc[LC_T12], lc[LC_T21], L.N, refl, tran);
+}
+
+// Leaf reflectance / transmittance from the plate transmissivity tau (prospect_5d.py:208-241).  Also
+// used by the FP32 mode for near-conservative plates, where the Stokes system is ill-conditioned in
+// 1 - r - t and single precision cannot hold the leaf absorptance 1 - refl - tran.
+__device__ __forceinline__ void leaf_from_tau(double tau, double t_alph, double t12, double t21, double N,
+                                              double& refl, double& tran) {
   const double r_alph = 1.0 - t_alph, r12 = 1.0 - t12, r21 = 1.0 - t21;
 
   // one plate, prospect_5d.py:208-214
@@ -538,7 +548,7 @@ __device__ __forceinline__ void prospect_point(const LeafPar& L, const double* l
 
   // Stokes system for the remaining N-1 plates, prospect_5d.py:219-230
   double Rsub, Tsub;
-  const double Nm1 = L.N - 1.0;
+  const double Nm1 = N - 1.0;
   if (r + t >= 1.0) {  // zero absorption, prospect_5d.py:233-235
     Tsub = t * rcp_fast(t + (1.0 - t) * Nm1);
     Rsub = 1.0 - Tsub;

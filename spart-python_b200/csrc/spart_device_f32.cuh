@@ -41,47 +41,54 @@ __device__ __forceinline__ float one_minus_exp(float z) {
 __device__ __forceinline__ float fexp(float x) { return __expf(x); }
 __device__ __forceinline__ float flog(float x) { return __logf(x); }
 
+// Degree-7 Chebyshev interpolants on the intervals of the FP64 tables (tools/gen_tau_coeffs.py:
+// relative error <= 9e-8 with float coefficients, i.e. float epsilon; the FP64 tables are degree 16).
+__constant__ float c_tauf_coef[SPART_TAU_NINT][SPART_TAUF_DEG + 1];
+
 struct TauTableF {
-  float coef[SPART_TAU_NINT][SPART_TAU_DEG + 1];
+  float coef[SPART_TAU_NINT][SPART_TAUF_DEG + 1];
   float mid[SPART_TAU_NINT];
   float invhalf[SPART_TAU_NINT];
 };
 
 __device__ __forceinline__ void load_tau_table_f(TauTableF* s) {
   float* dst = reinterpret_cast<float*>(s);
-  const int ncoef = SPART_TAU_NINT * (SPART_TAU_DEG + 1);
+  const int ncoef = SPART_TAU_NINT * (SPART_TAUF_DEG + 1);
   for (int i = threadIdx.x; i < ncoef + 2 * SPART_TAU_NINT; i += blockDim.x) {
-    double v;
-    if (i < ncoef) v = (&c_tau_coef[0][0])[i];
-    else if (i < ncoef + SPART_TAU_NINT) v = c_tau_mid[i - ncoef];
-    else v = c_tau_invhalf[i - ncoef - SPART_TAU_NINT];
-    dst[i] = (float)v;
+    float v;
+    if (i < ncoef) v = (&c_tauf_coef[0][0])[i];
+    else if (i < ncoef + SPART_TAU_NINT) v = (float)c_tau_mid[i - ncoef];
+    else v = (float)c_tau_invhalf[i - ncoef - SPART_TAU_NINT];
+    dst[i] = v;
   }
 }
 
-// tau(K) = (1-K) e^-K + K^2 E1(K), prospect_5d.py:182-196 (see plate_tau in spart_device.cuh)
-__device__ __forceinline__ float plate_tau_f(float K, const TauTableF* tab) {
+// tau(K) = (1-K) e^-K + K^2 E1(K), prospect_5d.py:182-196 (see plate_tau in spart_device.cuh).
+// Returns 1 - tau: for a weakly absorbing plate (K << 1) that is the quantity the leaf absorptance
+// hangs on, and it is formed without cancellation as (1 - e^-K) + K e^-K - K^2 E1(K).
+__device__ __forceinline__ float plate_one_minus_tau_f(float K, const TauTableF* tab) {
   const float emk = fexp(-K);
-  const float t = rcp(K);
   int idx;
-  float u;
+  float u, t = 0.0f;
   if (K < 1.0f) {
     idx = 0;
     u = 2.0f * K - 1.0f;
   } else {
+    t = rcp(K);
     const int e = (__float_as_int(K) >> 23) - 127;
     idx = min(e + 1, SPART_TAU_NINT - 1);
     u = (t - tab->mid[idx]) * tab->invhalf[idx];
   }
   const float* c = tab->coef[idx];
-  float p = c[SPART_TAU_DEG];
+  float p = c[SPART_TAUF_DEG];
 #pragma unroll
-  for (int i = SPART_TAU_DEG - 1; i >= 0; --i) p = fmaf(p, u, c[i]);
+  for (int i = SPART_TAUF_DEG - 1; i >= 0; --i) p = fmaf(p, u, c[i]);
   if (K < 1.0f) {
     const float e1 = fmaf(K, p, -0.57721566490153286061f - flog(K));
-    return (1.0f - K) * emk + K * K * e1;
+    const float ome = (K < 0.05f) ? K * (1.0f - K * (0.5f - K * (1.0f / 6.0f - K * (1.0f / 24.0f)))) : 1.0f - emk;
+    return fmaf(K, emk - K * e1, ome);
   }
-  return emk * t * p;
+  return 1.0f - emk * t * p;
 }
 
 struct LeafParF {
@@ -105,42 +112,51 @@ __device__ __forceinline__ LeafParF load_leaf_f(const ParamsT<T>& P, int64_t s) 
   return L;
 }
 
-// prospect_5d.py:117-246 at one wavelength
+// prospect_5d.py:117-246 at one wavelength.  Besides refl / tran the leaf absorptance
+// absorb = 1 - refl - tran is returned: the canopy solution depends on it (m^2 = absorb (a + sigb),
+// sailh.py:151) and for near-conservative leaves (NIR plateau, refl + tran > 0.98) a float difference of
+// refl and tran would lose it.  When the single plate is near-conservative (r + t > 0.9) the N-layer
+// Stokes system (prospect_5d.py:219-241), ill-conditioned in 1 - r - t, is solved in FP64 from the
+// float plate transmissivity (B200 runs FP64 at half the FP32 rate, and only the NIR bands take this path).
 __device__ __forceinline__ void prospect_point_f(const LeafParF& L, const float* lc, const TauTableF* tab,
-                                                 float& refl, float& tran) {
+                                                 float& refl, float& tran, float& absorb) {
   const float Ksum = L.Cab * lc[LC_KAB] + L.Cca * lc[LC_KCA] + L.Cdm * lc[LC_KDM] + L.Cw * lc[LC_KW] +
                      L.Cs * lc[LC_KS] + L.Cant * lc[LC_KANT] + L.CBC * lc[LC_CBC] + L.PROT * lc[LC_PROT];
   const float Kall = Ksum * L.invN;
-  float tau = 1.0f;
-  if (Kall > 0.0f) tau = plate_tau_f(Kall, tab);
+  float omt = 0.0f;
+  if (Kall > 0.0f) omt = plate_one_minus_tau_f(Kall, tab);
+  const float tau = 1.0f - omt;
   const float t_alph = lc[LC_TALPH], t12 = lc[LC_T12], t21 = lc[LC_T21];
   const float r_alph = 1.0f - t_alph, r12 = 1.0f - t12, r21 = 1.0f - t21;
   const float tt21 = tau * t21;
   const float inv_d1 = rcp(1.0f - r21 * r21 * tau * tau);
-  const float Ta = t_alph * tt21 * inv_d1;
-  const float Ra = r_alph + r21 * tau * Ta;
   const float t = t12 * tt21 * inv_d1;
   const float r = r12 + r21 * tau * t;
-  float Rsub, Tsub;
-  const float Nm1 = L.N - 1.0f;
-  if (r + t >= 1.0f) {
-    Tsub = t * rcp(t + (1.0f - t) * Nm1);
-    Rsub = 1.0f - Tsub;
-  } else {
-    const float D = fsqrt((1.0f + r + t) * (1.0f + r - t) * (1.0f - r + t) * (1.0f - r - t));
-    const float rq = r * r, tq = t * t;
-    const float a = (1.0f + rq - tq + D) * rcp(2.0f * r);
-    const float b = (1.0f - rq + tq + D) * rcp(2.0f * t);
-    const float bNm1 = (Nm1 == 0.0f) ? 1.0f : fexp(Nm1 * flog(b));
-    const float bN2 = bNm1 * bNm1;
-    const float a2 = a * a;
-    const float inv_d2 = rcp(a2 * bN2 - 1.0f);
-    Rsub = a * (bN2 - 1.0f) * inv_d2;
-    Tsub = bNm1 * (a2 - 1.0f) * inv_d2;
+  if (r + t > 0.9f) {
+    double rd, td;
+    leaf_from_tau(1.0 - (double)omt, (double)t_alph, (double)t12, (double)t21, (double)L.N, rd, td);
+    refl = (float)rd;
+    tran = (float)td;
+    absorb = (float)(1.0 - rd - td);
+    return;
   }
+  const float Ta = t_alph * tt21 * inv_d1;
+  const float Ra = r_alph + r21 * tau * Ta;
+  const float Nm1 = L.N - 1.0f;
+  const float D = fsqrt((1.0f + r + t) * (1.0f + r - t) * (1.0f - r + t) * (1.0f - r - t));
+  const float rq = r * r, tq = t * t;
+  const float a = (1.0f + rq - tq + D) * rcp(2.0f * r);
+  const float b = (1.0f - rq + tq + D) * rcp(2.0f * t);
+  const float bNm1 = (Nm1 == 0.0f) ? 1.0f : fexp(Nm1 * flog(b));
+  const float bN2 = bNm1 * bNm1;
+  const float a2 = a * a;
+  const float inv_d2 = rcp(a2 * bN2 - 1.0f);
+  const float Rsub = a * (bN2 - 1.0f) * inv_d2;
+  const float Tsub = bNm1 * (a2 - 1.0f) * inv_d2;
   const float inv_d3 = rcp(1.0f - Rsub * r);
   tran = Ta * Tsub * inv_d3;
   refl = Ra + Ta * Rsub * t * inv_d3;
+  absorb = 1.0f - refl - tran;
 }
 
 struct SoilParF {
@@ -179,8 +195,16 @@ __device__ __forceinline__ float sail_J1_f(float m, float k, float LAI, float em
 }
 
 // sailh.py:99-105, 142-233 at one wavelength
-__device__ __forceinline__ void sailh_point_f(const CanopyGeoF& G, float rho, float tau, float rs, float& rso,
-                                              float& rdo, float& rsd, float& rdd) {
+// Single-precision forms (tools/fp32_study.py measures each against the float64 oracle): rinf =
+// sigb / (a + m) and 1 - rinf^2 = 2 m / (a + m) * rinf replace (a - m) / sigb and the difference, which
+// cancel for dark (a ~ m) and for bright (rinf ~ 1) leaves; 1 - e^-x terms switch to their series for
+// small x; m^2 = absorb (a + sigb) takes the leaf absorptance from PROSPECT instead of 1 - rho - tau.
+__device__ __forceinline__ float omx(float z, float ez) {   // 1 - e^z for z <= 0, ez = e^z already known
+  return (z > -0.05f) ? -z * (1.0f + z * (0.5f + z * (1.0f / 6.0f + z * (1.0f / 24.0f)))) : 1.0f - ez;
+}
+
+__device__ __forceinline__ void sailh_point_f(const CanopyGeoF& G, float rho, float tau, float absorb, float rs,
+                                              float& rso, float& rdo, float& rsd, float& rdd) {
   const float k = G.k, K = G.K, bf = G.bf, LAI = G.LAI;
   const float sdb = 0.5f * (k + bf), sdf = 0.5f * (k - bf);
   const float ddb = 0.5f * (1.0f + bf), ddf = 0.5f * (1.0f - bf);
@@ -193,34 +217,36 @@ __device__ __forceinline__ void sailh_point_f(const CanopyGeoF& G, float rho, fl
   const float vf = dof * rho + dob * tau;
   const float w = G.sob * rho + G.sof * tau;
   const float a = 1.0f - sigf;
-  // a^2 - sigb^2 = (1 - rho - tau)(a + sigb): the first factor is formed directly (sigf + sigb = rho + tau)
-  const float m = fsqrt((1.0f - rho - tau) * (a + sigb));
-  const float rinf = (a - m) * rcp(sigb);
+  // a^2 - sigb^2 = (1 - rho - tau)(a + sigb) (sigf + sigb = rho + tau)
+  const float m = fsqrt(absorb * (a + sigb));
+  const float inv_apm = rcp(a + m);
+  const float rinf = sigb * inv_apm;                 // (a - m) / sigb, since (a - m)(a + m) = sigb^2
   const float rinf2 = rinf * rinf;
+  const float omr2 = 2.0f * m * inv_apm;             // 1 - rinf^2 = ((a + m)^2 - sigb^2) / (a + m)^2 = 2 m / (a + m)
   const float e1 = fexp(-m * LAI);
   const float e2 = e1 * e1;
   const float tau_ss = G.tau_ss, tau_oo = G.tau_oo;
   const float inv_km = rcp(k + m), inv_Km = rcp(K + m);
   const float J1k = sail_J1_f(m, k, LAI, e1, tau_ss);
-  const float J2k = (1.0f - tau_ss * e1) * inv_km;
+  const float J2k = omx(-(k + m) * LAI, tau_ss * e1) * inv_km;
   const float J1K = sail_J1_f(m, K, LAI, e1, tau_oo);
-  const float J2K = (1.0f - tau_oo * e1) * inv_Km;
+  const float J2K = omx(-(K + m) * LAI, tau_oo * e1) * inv_Km;
   const float re = rinf * e1;
-  const float inv_den = rcp((1.0f - rinf2) * (1.0f + rinf2));
+  const float inv_den = rcp(omr2 * (1.0f + rinf2));
   const float s1 = sf + rinf * sb, s2 = sf * rinf + sb;
   const float v1 = vf + rinf * vb, v2 = vf * rinf + vb;
   const float Pss = s1 * J1k, Qss = s2 * J2k;
   const float Poo = v1 * J1K, Qoo = v2 * J2K;
   const float Z = G.Z;
-  const float tau_dd = (1.0f - rinf2) * e1 * inv_den;
-  const float rho_dd = rinf * (1.0f - e2) * inv_den;
+  const float tau_dd = omr2 * e1 * inv_den;
+  const float rho_dd = rinf * omx(-2.0f * m * LAI, e2) * inv_den;
   const float tau_sd = (Pss - re * Qss) * inv_den;
   const float tau_do = (Poo - re * Qoo) * inv_den;
   const float rho_sd = (Qss - re * Pss) * inv_den;
   const float rho_do = (Qoo - re * Poo) * inv_den;
   const float T1 = v2 * s1 * (Z - J1k * tau_oo) * inv_Km + v1 * s2 * (Z - J1K * tau_ss) * inv_km;
   const float T2 = -(Qoo * rho_sd + Poo * tau_sd) * rinf;
-  const float rho_sod = (T1 + T2) * rcp(1.0f - rinf2);
+  const float rho_sod = (T1 + T2) * rcp(omr2);
   const float rho_so = rho_sod + w * G.sumpso;
   const float rs_den = rs * rcp(1.0f - rs * rho_dd);
   rso = rho_so + rs * G.pso2w + ((tau_sd + tau_ss * rs * rho_dd) * tau_oo + (tau_sd + tau_ss) * tau_do) * rs_den;

@@ -1137,6 +1137,7 @@ band_kernel_f32(const ParamsT<TIO> P, int64_t n, const float* __restrict__ rec,
   const int b0 = blockIdx.x * kBandChunk;
   const int nbc = min(kBandChunk, nb - b0);
   load_tau_table_f(&s_tau);
+  exp_table_load();       // the FP64 Stokes solve of near-conservative leaves uses the table-driven exp
   for (int i = threadIdx.x; i < nbc * BT_COUNT; i += blockDim.x)
     (&s_bt[0][0])[i] = (float)band_table[(size_t)b0 * BT_COUNT + i];
   __syncthreads();
@@ -1173,10 +1174,10 @@ band_kernel_f32(const ParamsT<TIO> P, int64_t n, const float* __restrict__ rec,
 #pragma unroll 1
     for (int pt = 0; pt < npts; ++pt) {
       const float* lc = &bt[BT_LC0 + pt * LC_COUNT];
-      float refl, tran, a0, a1, a2, a3;
-      prospect_point_f(L, lc, &s_tau, refl, tran);
+      float refl, tran, absorb, a0, a1, a2, a3;
+      prospect_point_f(L, lc, &s_tau, refl, tran, absorb);
       const float rwet = bsm_point_f(S, lc);
-      sailh_point_f(G, refl, tran, rwet, a0, a1, a2, a3);
+      sailh_point_f(G, refl, tran, absorb, rwet, a0, a1, a2, a3);
       if (pt == 0) {
         rso = a0; rdo = a1; rsd = a2; rdd = a3;
       } else {
@@ -1329,6 +1330,7 @@ static int init_device_constants(int device) {
   CUDA_TRY(cudaMemcpyToSymbol(c_tau_coef, SPART_TAU_COEF_H, sizeof(SPART_TAU_COEF_H)));
   CUDA_TRY(cudaMemcpyToSymbol(c_tau_mid, SPART_TAU_MID_H, sizeof(SPART_TAU_MID_H)));
   CUDA_TRY(cudaMemcpyToSymbol(c_tau_invhalf, SPART_TAU_INVHALF_H, sizeof(SPART_TAU_INVHALF_H)));
+  CUDA_TRY(cudaMemcpyToSymbol(f32::c_tauf_coef, SPART_TAUF_COEF_H, sizeof(SPART_TAUF_COEF_H)));
   double sl[13], cl[13];
   for (int i = 0; i < 13; ++i) {  // litab (sailh.py:49): 5,15,...,75, 81,83,...,89 degrees
     const double li = (i < 8) ? 5.0 + 10.0 * i : 81.0 + 2.0 * (i - 8);

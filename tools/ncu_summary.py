@@ -53,6 +53,10 @@ def main(path, units=1e6):
             "warps_active_pct": g(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
             "fp64_pipe_pct": g(r, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
             "issue_active_pct": g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "fma_pipe_pct": g(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "xu_pipe_pct": g(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+            "alu_pipe_pct": g(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "lsu_pipe_pct": g(r, "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
             "threads_per_inst": g(r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
             "warp_inst": g(r, "smsp__inst_executed.sum"),
             "fp64_thread_inst_per_unit": {k: v / units for k, v in d.items()},
