@@ -165,7 +165,7 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_
 
 /* Same computation with HOST buffers: params_host [SPART_NPAR][ld] and out_host (layout and
  * element type as above, SPART_OUT_ELEMS elements) are ordinary host memory.  The batch is cut
- * into chunks of 64 Ki samples that are pipelined over three internal streams (H2D, kernels,
+ * into chunks of 128 Ki samples that are pipelined over four internal streams (H2D, kernels,
  * D2H).  Pinned or registered buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are
  * DMA'd directly; pageable buffers (plain NumPy arrays) are staged through internal pinned
  * buffers by a small pool of copy threads (SPART_HOST_THREADS, default 8), because an asynchronous

@@ -185,14 +185,14 @@ struct SpartCtx {
   // host-buffer path: lazily created slots (device params / workspace / output, and pinned host
   // staging buffers that are only allocated when the caller's memory is pageable)
   std::mutex mu;
-  static const int kSlots = 3;
-  cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
-  cudaEvent_t slot_done[kSlots] = {nullptr, nullptr, nullptr};
-  void* slot_params[kSlots] = {nullptr, nullptr, nullptr};
-  double* slot_rec[kSlots] = {nullptr, nullptr, nullptr};
-  void* slot_out[kSlots] = {nullptr, nullptr, nullptr};
-  void* stage_in[kSlots] = {nullptr, nullptr, nullptr};     // pinned host
-  void* stage_out[kSlots] = {nullptr, nullptr, nullptr};    // pinned host
+  static const int kSlots = 4;
+  cudaStream_t streams[kSlots] = {};
+  cudaEvent_t slot_done[kSlots] = {};
+  void* slot_params[kSlots] = {};
+  double* slot_rec[kSlots] = {};
+  void* slot_out[kSlots] = {};
+  void* stage_in[kSlots] = {};     // pinned host
+  void* stage_out[kSlots] = {};    // pinned host
   int64_t slot_cap = 0;        // samples per slot
   size_t slot_out_cap = 0;     // bytes of output per slot
   size_t stage_in_cap = 0, stage_out_cap = 0;   // bytes
@@ -1927,10 +1927,16 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
   const size_t elt = (flags & SPART_FLAG_F32_IO) ? sizeof(float) : sizeof(double);
   const bool compact = (flags & SPART_FLAG_COMPACT_OUT) != 0;
   const int nout = compact ? 2 : SPART_NOUT;
-  // chunk so that three slots pipeline H2D / kernels / D2H (64 Ki samples: ~14 MB in, ~20 MB out
-  // per chunk for 13 bands, small enough that pipeline fill/drain is a few percent of a 1M batch);
-  // cap the per-slot output at ~256 MB for many-band sensors
-  int64_t chunk = 1 << 16;
+  // chunks pipeline H2D / kernels / D2H over the slots.  128 Ki samples per chunk: large enough that a
+  // chunk's kernels nearly fill the GPU (1024 blocks of the band kernel; with 64 Ki the three kernels of a
+  // chunk ran at a quarter of their throughput and the pipeline became kernel-bound), small enough that
+  // the unoverlapped first H2D and last D2H stay ~10 % of a 1M batch; cap the per-slot output at ~256 MB
+  // for many-band sensors.  SPART_HOST_CHUNK overrides (tuning).
+  int64_t chunk = 1 << 17;
+  if (const char* e = getenv("SPART_HOST_CHUNK")) {
+    const long long v = atoll(e);
+    if (v >= 1024) chunk = v;
+  }
   const int64_t cap_by_out = ((int64_t)256 << 20) / ((int64_t)nb * SPART_NOUT * 8);
   if (chunk > cap_by_out) chunk = cap_by_out > 1024 ? cap_by_out : 1024;
   if (chunk > n) chunk = n;
