@@ -180,8 +180,13 @@ struct SpartCtx {
   // optional SRF tables per sensor (band_mode "srf"): per band the number of non-zero weights and
   // its offset into the concatenated (wavelength index, normalised weight) lists; nullptr when
   // the sensor was created without them
-  std::vector<int32_t*> d_srf_idx, d_srf_len, d_srf_off;
-  std::vector<double*> d_srf_w;
+  struct SrfDev {                       // device arrays behind one SrfPlan (all nullptr: no SRF tables)
+    int n_wl = 0, n_slots = 0;
+    int32_t *wl_idx = nullptr, *pair_off = nullptr, *pair_slot = nullptr, *fin_off = nullptr, *fin_band = nullptr,
+            *fin_slot = nullptr;
+    double* pair_w = nullptr;
+  };
+  std::vector<SrfDev> srf;
   // host-buffer path: lazily created slots (device params / workspace / output, and pinned host
   // staging buffers that are only allocated when the caller's memory is pageable)
   std::mutex mu;
@@ -853,25 +858,42 @@ band_kernel(const Params P, int64_t n, const double* __restrict__ rec,
 // Band kernel of the SRF mode (SPART_FLAG_SRF_BANDS): the four canopy reflectances of a band are
 // the spectral-response-weighted means over the band's support (calculate_spectral_convolution,
 // SPART.py:358-396, applied to canopyopt) instead of np.interp samples at the band centre.
-// blockIdx.x = band, blockIdx.y = sample tile, thread = sample; the (wavelength, weight) list is
-// walked in chunks of kSrfChunk entries whose constants and weights are staged in shared memory.
+//
+// Bands overlap (TerraAqua-MODIS lists 2006 (wavelength, weight) pairs on 694 distinct wavelengths),
+// so the leaf / soil / canopy model is evaluated ONCE per distinct wavelength, in ascending order, and
+// its four reflectances are added into every band that contains the wavelength.  A band's accumulators
+// live in a shared-memory slot (one column per thread); spart_create assigns slots by interval colouring
+// (bands whose supports overlap get different slots: a handful suffices) and lists, per wavelength, the
+// (slot, weight) pairs to add and the bands that are complete after it: for those SMAC + TOC->TOA run
+// right away and the slot is cleared.  Each band still sums its samples in ascending wavelength order.
+// thread = sample, block = sample tile; everything about wavelengths / bands is warp-uniform.
 constexpr int kSrfChunk = 32;
+
+struct SrfPlan {               // device pointers, built by spart_create
+  int n_wl;                    // distinct wavelengths, ascending
+  int n_slots;                 // accumulator slots (max. number of simultaneously open bands + 1 spare)
+  const int32_t* wl_idx;       // [n_wl] index into 400..2400 nm
+  const int32_t* pair_off;     // [n_wl + 1] offsets into pair_slot / pair_w
+  const int32_t* pair_slot;
+  const double* pair_w;        // normalised SRF weights
+  const int32_t* fin_off;      // [n_wl + 1] offsets into fin_band / fin_slot: bands complete after wavelength i
+  const int32_t* fin_band;
+  const int32_t* fin_slot;
+};
 
 __global__ void __launch_bounds__(kBandThreads, SPART_SRF_MINBLOCKS)
 band_kernel_srf(const Params P, int64_t n, const double* __restrict__ rec,
-                const double* __restrict__ band_table, const double* __restrict__ lc_table,
-                const int32_t* __restrict__ srf_idx, const int32_t* __restrict__ srf_len,
-                const int32_t* __restrict__ srf_off, const double* __restrict__ srf_w, int nb,
-                double* __restrict__ out, int compact) {
+                const double* __restrict__ band_table, const double* __restrict__ lc_table, const SrfPlan plan,
+                int nb, double* __restrict__ out, int compact) {
+  extern __shared__ double s_acc[];            // [n_slots][4][kBandThreads]
   __shared__ TauTable s_tau;
-  __shared__ double s_bt[BT_COUNT];
   __shared__ double s_lc[kSrfChunk][LC_COUNT];
-  __shared__ double s_w[kSrfChunk];
-  const int b = blockIdx.x;
+  __shared__ int s_poff[kSrfChunk + 1], s_foff[kSrfChunk + 1];
+  const int t = threadIdx.x;
   load_tau_table(&s_tau);
   exp_table_load();
-  for (int i = threadIdx.x; i < BT_COUNT; i += blockDim.x) s_bt[i] = band_table[(size_t)b * BT_COUNT + i];
-  const int64_t s_raw = (int64_t)blockIdx.y * kBandThreads + threadIdx.x;
+  for (int i = 0; i < plan.n_slots * 4; ++i) s_acc[i * kBandThreads + t] = 0.0;
+  const int64_t s_raw = (int64_t)blockIdx.x * kBandThreads + t;
   const bool valid = s_raw < n;
   const int64_t s = valid ? s_raw : n - 1;
   const LeafPar L = load_leaf(P, s);
@@ -883,57 +905,72 @@ band_kernel_srf(const Params P, int64_t n, const double* __restrict__ rec,
     const double v[17] = {S.f1, S.f2, S.f3, S.mu, S.emu, S.film, G.LAI, G.k, G.K, G.bf, G.sob, G.sof,
                           G.tau_ss, G.tau_oo, G.sumpso, G.pso2w, G.Z};
 #pragma unroll
-    for (int i = 0; i < 17; ++i) s_st[i][threadIdx.x] = v[i];
+    for (int i = 0; i < 17; ++i) s_st[i][t] = v[i];
   }
-  const int len = srf_len[b];
-  const double* wts = srf_w + srf_off[b];
-  const int32_t* wix = srf_idx + srf_off[b];
-  double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
-  __syncthreads();      // s_bt / exp table complete even for a band without SRF samples (len == 0)
-  for (int c0 = 0; c0 < len; c0 += kSrfChunk) {
-    const int m = min(kSrfChunk, len - c0);
+  const double etscale = rec[R_ETSCALE * n + s];
+  const int nout = compact ? 2 : SPART_NOUT;
+  if (compact && valid) out[(size_t)n * nb * 2 + s] = etscale;
+
+  for (int c0 = 0; c0 < plan.n_wl; c0 += kSrfChunk) {
+    const int m = min(kSrfChunk, plan.n_wl - c0);
     __syncthreads();
-    for (int i = threadIdx.x; i < m * LC_COUNT; i += blockDim.x)
-      s_lc[i / LC_COUNT][i % LC_COUNT] = lc_table[(size_t)(i % LC_COUNT) * SPART_NWL + wix[c0 + i / LC_COUNT]];
-    for (int i = threadIdx.x; i < m; i += blockDim.x) s_w[i] = wts[c0 + i];
+    for (int i = t; i < m * LC_COUNT; i += blockDim.x)
+      s_lc[i / LC_COUNT][i % LC_COUNT] = lc_table[(size_t)(i % LC_COUNT) * SPART_NWL + plan.wl_idx[c0 + i / LC_COUNT]];
+    for (int i = t; i <= m; i += blockDim.x) {
+      s_poff[i] = plan.pair_off[c0 + i];
+      s_foff[i] = plan.fin_off[c0 + i];
+    }
     __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < m; ++j) {
-      const double wj = s_w[j];
       double refl, tran, kchl, rwet, rdry, a0, a1, a2, a3;
       prospect_point<false>(L, s_lc[j], &s_tau, refl, tran, kchl);
       {
         volatile double(*st)[kBandThreads] = s_st;
-        const int t = threadIdx.x;
         S.f1 = st[0][t]; S.f2 = st[1][t]; S.f3 = st[2][t]; S.mu = st[3][t]; S.emu = st[4][t]; S.film = st[5][t];
         bsm_point(S, s_lc[j], rwet, rdry);
         G.LAI = st[6][t]; G.k = st[7][t]; G.K = st[8][t]; G.bf = st[9][t]; G.sob = st[10][t]; G.sof = st[11][t];
         G.tau_ss = st[12][t]; G.tau_oo = st[13][t]; G.sumpso = st[14][t]; G.pso2w = st[15][t]; G.Z = st[16][t];
         sailh_point(G, refl, tran, rwet, a0, a1, a2, a3);
       }
-      rso = fma(wj, a0, rso);
-      rdo = fma(wj, a1, rdo);
-      rsd = fma(wj, a2, rsd);
-      rdd = fma(wj, a3, rdd);
+      // add into every band that contains this wavelength (own column of the slot: no synchronisation)
+#pragma unroll 1
+      for (int p = s_poff[j]; p < s_poff[j + 1]; ++p) {
+        const double w = __ldg(plan.pair_w + p);
+        double* acc = s_acc + (size_t)__ldg(plan.pair_slot + p) * 4 * kBandThreads + t;
+        acc[0 * kBandThreads] = fma(w, a0, acc[0 * kBandThreads]);     // rso
+        acc[1 * kBandThreads] = fma(w, a1, acc[1 * kBandThreads]);     // rdo
+        acc[2 * kBandThreads] = fma(w, a2, acc[2 * kBandThreads]);     // rsd
+        acc[3 * kBandThreads] = fma(w, a3, acc[3 * kBandThreads]);     // rdd
+      }
+      // bands whose last wavelength this was: atmosphere + TOC -> TOA, then the slot is free again
+#pragma unroll 1
+      for (int f = s_foff[j]; f < s_foff[j + 1]; ++f) {
+        const int b = __ldg(plan.fin_band + f);
+        double* acc = s_acc + (size_t)__ldg(plan.fin_slot + f) * 4 * kBandThreads + t;
+        const double rso = acc[0 * kBandThreads], rdo = acc[1 * kBandThreads], rsd = acc[2 * kBandThreads],
+                     rdd = acc[3 * kBandThreads];
+        acc[0 * kBandThreads] = acc[1 * kBandThreads] = acc[2 * kBandThreads] = acc[3 * kBandThreads] = 0.0;
+        AtmSample A;
+        A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
+        A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s];
+        A.lpeq = rec[R_LPEQ * n + s];
+        A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
+        A.taup550 = P.at(P_AOT, s);
+        A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
+        A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
+        const double* bt = band_table + (size_t)b * BT_COUNT;
+        double R_TOC, R_TOA, L_TOA;
+        smac_toa_band(A, bt + BT_SMAC, __ldg(bt + BT_CONVEA), etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
+        if (valid) {
+          double* o = out + ((size_t)s * nb + b) * nout;
+          o[0] = R_TOC;
+          o[1] = R_TOA;
+          if (!compact) o[2] = L_TOA;
+        }
+      }
     }
   }
-  if (!valid) return;
-  AtmSample A;
-  A.us = rec[R_US * n + s]; A.uv = rec[R_UV * n + s]; A.m = rec[R_M * n + s]; A.Peq = rec[R_PEQ * n + s];
-  A.lo3 = rec[R_LO3 * n + s]; A.lh2o = rec[R_LH2O * n + s]; A.lm = rec[R_LM * n + s]; A.lpeq = rec[R_LPEQ * n + s];
-  A.cksi = rec[R_CKSI * n + s]; A.ksiD = rec[R_KSID * n + s]; A.ray_phase = rec[R_RAYPH * n + s];
-  A.taup550 = P.at(P_AOT, s);
-  A.inv_us = rec[R_INVUS * n + s]; A.inv_uv = rec[R_INVUV * n + s];
-  A.inv_1pus = rec[R_INV1PUS * n + s]; A.inv_1puv = rec[R_INV1PUV * n + s]; A.aa3 = rec[R_AA3 * n + s];
-  double R_TOC, R_TOA, L_TOA;
-  const double etscale = rec[R_ETSCALE * n + s];
-  smac_toa_band(A, &s_bt[BT_SMAC], s_bt[BT_CONVEA], etscale, rso, rdo, rdd, rsd, R_TOC, R_TOA, L_TOA);
-  const int nout = compact ? 2 : SPART_NOUT;
-  double* o = out + ((size_t)s * nb + b) * nout;
-  o[0] = R_TOC;
-  o[1] = R_TOA;
-  if (!compact) o[2] = L_TOA;
-  else if (b == 0) out[(size_t)n * nb * 2 + s] = etscale;
 }
 
 // SMAC alone (the reference's SMAC(angles, atm, coefs), smac.py:14-213): the nine
@@ -1019,9 +1056,21 @@ geometry_kernel_f32(const ParamsT<TIO> P, int64_t n, float* __restrict__ rec, in
   sincosf(tts * (SPART_PI_F / 180.0f), &sin_tts, &cos_tts);
   sincosf(tto * (SPART_PI_F / 180.0f), &sin_tto, &cos_tto);
   const float inv_cs = rcp(cos_tts), inv_co = rcp(cos_tto);
-  const float tan_tts = sin_tts * inv_cs, tan_tto = sin_tto * inv_co;
   const float cos_psi = cosf(psi_rad);
-  const float dso = fsqrt(fmaxf(0.0f, tan_tts * tan_tts + tan_tto * tan_tto - 2.0f * tan_tts * tan_tto * cos_psi));
+  // dso (sailh.py:78) is a difference of O(1) terms that vanishes in the hot spot: a degree away from it single
+  // precision has no digits left, so this one per-sample scalar is formed in FP64 from the angles as given
+  float dso;
+  {
+    double sd, cd, so_, co_, sp, cp;
+    sincos_small(tts_d * SPART_DEG2RAD, sd, cd);
+    sincos_small(tto_d * SPART_DEG2RAD, so_, co_);
+    const double psi_d = fabs(rel_d - 360.0 * rint(rel_d / 360.0));
+    sincos_small(psi_d * SPART_DEG2RAD, sp, cp);
+    (void)sp;
+    const double ts = sd / cd, to = so_ / co_;
+    const double d2 = ts * ts + to * to - 2.0 * ts * to * cp;
+    dso = (float)sqrt(fmax(d2, 0.0));
+  }
   const float inv_cc = SPART_PI_F * inv_cs * inv_co;
 
   if (uniform_geometry) {
@@ -1393,14 +1442,115 @@ int spart_destroy(SpartCtx* ctx) {
   for (auto& pe : ctx->prof_pending) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
   for (auto& pe : ctx->prof_free) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
   for (double* d : ctx->d_band) cudaFree(d);
-  for (auto* d : ctx->d_srf_idx) if (d) cudaFree(d);
-  for (auto* d : ctx->d_srf_len) if (d) cudaFree(d);
-  for (auto* d : ctx->d_srf_off) if (d) cudaFree(d);
-  for (auto* d : ctx->d_srf_w) if (d) cudaFree(d);
+  for (auto& v : ctx->srf) {
+    cudaFree(v.wl_idx); cudaFree(v.pair_off); cudaFree(v.pair_slot); cudaFree(v.fin_off); cudaFree(v.fin_band);
+    cudaFree(v.fin_slot); cudaFree(v.pair_w);
+  }
   if (ctx->d_lc) cudaFree(ctx->d_lc);
   delete ctx;
   return SPART_OK;
 }
+
+}  // extern "C"
+
+// SRF band mode: turn the per-band (wavelength, weight) lists into the schedule band_kernel_srf walks --
+// distinct wavelengths in ascending order, per wavelength the (accumulator slot, weight) pairs to add and
+// the bands that are complete after it.  Slots are an interval colouring of the bands' supports.
+template <typename T>
+static int upload(const std::vector<T>& v, T** d) {
+  CUDA_TRY(cudaMalloc(d, sizeof(T) * (v.empty() ? 1 : v.size())));
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(*d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return SPART_OK;
+}
+
+constexpr int kSrfMaxSlots = 24;      // 24 x 4 x 128 doubles = 96 KB of accumulators at most
+
+static int build_srf_plan(const SpartSensor& S, SpartCtx::SrfDev& dev) {
+  const int nb = S.n_bands;
+  std::vector<int64_t> off(nb + 1, 0);
+  for (int b = 0; b < nb; ++b) {
+    if (S.srf_len[b] < 0) return fail(SPART_EINVAL, "spart_create: negative SRF length%s");
+    off[b + 1] = off[b] + S.srf_len[b];
+  }
+  const int64_t total = off[nb];
+  std::vector<char> used(SPART_NWL, 0);
+  for (int64_t k = 0; k < total; ++k) {
+    if (S.srf_idx[k] < 0 || S.srf_idx[k] >= SPART_NWL)
+      return fail(SPART_EINVAL, "spart_create: SRF wavelength index outside 400..2400 nm%s");
+    used[S.srf_idx[k]] = 1;
+  }
+  std::vector<int32_t> wl_idx, pos(SPART_NWL, -1);
+  for (int w = 0; w < SPART_NWL; ++w)
+    if (used[w]) {
+      pos[w] = (int32_t)wl_idx.size();
+      wl_idx.push_back(w);
+    }
+  const int U = (int)wl_idx.size();
+  // first / last position of every band on the distinct-wavelength axis
+  std::vector<int> first(nb, U), last(nb, -1);
+  for (int b = 0; b < nb; ++b)
+    for (int64_t k = off[b]; k < off[b + 1]; ++k) {
+      const int q = pos[S.srf_idx[k]];
+      if (q < first[b]) first[b] = q;
+      if (q > last[b]) last[b] = q;
+    }
+  // interval colouring: walk the wavelengths, release the slots of finished bands, hand the lowest free
+  // slot to every band that starts
+  std::vector<int> slot(nb, -1), free_slots;
+  int n_slots = 0;
+  std::vector<std::vector<int>> starts(U + 1), ends(U + 1);
+  for (int b = 0; b < nb; ++b)
+    if (last[b] >= 0) {
+      starts[first[b]].push_back(b);
+      ends[last[b]].push_back(b);
+    }
+  for (int q = 0; q < U; ++q) {
+    for (int b : starts[q]) {
+      if (free_slots.empty()) free_slots.push_back(n_slots++);
+      slot[b] = free_slots.back();
+      free_slots.pop_back();
+    }
+    for (int b : ends[q]) free_slots.push_back(slot[b]);
+  }
+  const int spare = n_slots++;          // never accumulated into: bands without any SRF sample read zeros from it
+  if (n_slots > kSrfMaxSlots) return fail(SPART_EINVAL, "spart_create: too many overlapping bands for the SRF band mode%s");
+  // per wavelength: pairs in ascending band order (each band's own sum keeps its ascending wavelength order)
+  std::vector<std::vector<std::pair<int, double>>> pairs(U);
+  for (int b = 0; b < nb; ++b)
+    for (int64_t k = off[b]; k < off[b + 1]; ++k) pairs[pos[S.srf_idx[k]]].push_back({slot[b], S.srf_w[k]});
+  std::vector<int32_t> pair_off(U + 1, 0), pair_slot, fin_off(U + 1, 0), fin_band, fin_slot;
+  std::vector<double> pair_w;
+  for (int q = 0; q < U; ++q) {
+    for (auto& pr : pairs[q]) {
+      pair_slot.push_back(pr.first);
+      pair_w.push_back(pr.second);
+    }
+    pair_off[q + 1] = (int32_t)pair_slot.size();
+    for (int b : ends[q]) {
+      fin_band.push_back(b);
+      fin_slot.push_back(slot[b]);
+    }
+    if (q == U - 1)
+      for (int b = 0; b < nb; ++b)
+        if (last[b] < 0) {
+          fin_band.push_back(b);
+          fin_slot.push_back(spare);
+        }
+    fin_off[q + 1] = (int32_t)fin_band.size();
+  }
+  if (U == 0) return fail(SPART_EINVAL, "spart_create: SRF tables without a single sample%s");
+  dev.n_wl = U;
+  dev.n_slots = n_slots;
+  int rc;
+  if ((rc = upload(wl_idx, &dev.wl_idx)) || (rc = upload(pair_off, &dev.pair_off)) ||
+      (rc = upload(pair_slot, &dev.pair_slot)) || (rc = upload(pair_w, &dev.pair_w)) ||
+      (rc = upload(fin_off, &dev.fin_off)) || (rc = upload(fin_band, &dev.fin_band)) ||
+      (rc = upload(fin_slot, &dev.fin_slot)))
+    return rc;
+  return SPART_OK;
+}
+
+extern "C" {
 
 // body of spart_create; on any failure the caller releases the partially built context
 static int create_into(SpartCtx* ctx, const SpartTables* tables, const SpartSensor* sensors, int32_t n_sensors,
@@ -1429,31 +1579,12 @@ static int create_into(SpartCtx* ctx, const SpartTables* tables, const SpartSens
     // every vector gets its slot first, so that spart_destroy releases whatever was allocated
     ctx->d_band.push_back(nullptr);
     ctx->n_bands.push_back(S.n_bands);
-    ctx->d_srf_idx.push_back(nullptr);
-    ctx->d_srf_len.push_back(nullptr);
-    ctx->d_srf_off.push_back(nullptr);
-    ctx->d_srf_w.push_back(nullptr);
+    ctx->srf.emplace_back();
     CUDA_TRY(cudaMalloc(&ctx->d_band[i], bt.size() * sizeof(double)));
     CUDA_TRY(cudaMemcpy(ctx->d_band[i], bt.data(), bt.size() * sizeof(double), cudaMemcpyHostToDevice));
     if (S.srf_idx && S.srf_len && S.srf_w) {
-      std::vector<int32_t> off(S.n_bands);
-      int64_t total = 0;
-      for (int b = 0; b < S.n_bands; ++b) {
-        if (S.srf_len[b] < 0) return fail(SPART_EINVAL, "spart_create: negative SRF length%s");
-        off[b] = (int32_t)total;
-        total += S.srf_len[b];
-      }
-      for (int64_t k = 0; k < total; ++k)
-        if (S.srf_idx[k] < 0 || S.srf_idx[k] >= SPART_NWL)
-          return fail(SPART_EINVAL, "spart_create: SRF wavelength index outside 400..2400 nm%s");
-      CUDA_TRY(cudaMalloc(&ctx->d_srf_idx[i], sizeof(int32_t) * (total > 0 ? total : 1)));
-      CUDA_TRY(cudaMalloc(&ctx->d_srf_len[i], sizeof(int32_t) * S.n_bands));
-      CUDA_TRY(cudaMalloc(&ctx->d_srf_off[i], sizeof(int32_t) * S.n_bands));
-      CUDA_TRY(cudaMalloc(&ctx->d_srf_w[i], sizeof(double) * (total > 0 ? total : 1)));
-      CUDA_TRY(cudaMemcpy(ctx->d_srf_idx[i], S.srf_idx, sizeof(int32_t) * total, cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(ctx->d_srf_len[i], S.srf_len, sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(ctx->d_srf_off[i], off.data(), sizeof(int32_t) * S.n_bands, cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMemcpy(ctx->d_srf_w[i], S.srf_w, sizeof(double) * total, cudaMemcpyHostToDevice));
+      rc = build_srf_plan(S, ctx->srf[i]);
+      if (rc) return rc;
     }
   }
   return SPART_OK;
@@ -1540,7 +1671,7 @@ static int check_mode(const SpartCtx* ctx, int32_t sensor, int32_t precision, in
     return fail(SPART_EINVAL, "%s: SPART_FLAG_F32_IO needs SPART_FP32", who);
   if (flags & SPART_FLAG_SRF_BANDS) {
     if (precision != SPART_FP64) return fail(SPART_EINVAL, "%s: SRF band mode needs SPART_FP64", who);
-    if (!ctx->d_srf_w[sensor]) return fail(SPART_EINVAL, "%s: this sensor was created without SRF tables", who);
+    if (!ctx->srf[sensor].pair_w) return fail(SPART_EINVAL, "%s: this sensor was created without SRF tables", who);
   }
   return SPART_OK;
 }
@@ -1619,11 +1750,14 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_
     if (prof) CUDA_TRY(cudaEventRecord(pe.e[2], st));
     NvtxRange r("spart::bands");
     if (flags & SPART_FLAG_SRF_BANDS) {
-      dim3 sgrid((unsigned)nb, (unsigned)((n + kBandThreads - 1) / kBandThreads));
-      band_kernel_srf<<<sgrid, kBandThreads, 0, st>>>(P, n, rec, ctx->d_band[sensor], ctx->d_lc,
-                                                      ctx->d_srf_idx[sensor], ctx->d_srf_len[sensor],
-                                                      ctx->d_srf_off[sensor], ctx->d_srf_w[sensor], nb, out,
-                                                      compact ? 1 : 0);
+      const SpartCtx::SrfDev& v = ctx->srf[sensor];
+      const SrfPlan plan{v.n_wl, v.n_slots, v.wl_idx, v.pair_off, v.pair_slot, v.pair_w, v.fin_off, v.fin_band,
+                         v.fin_slot};
+      const size_t acc_bytes = sizeof(double) * v.n_slots * 4 * kBandThreads;
+      if (acc_bytes > 16 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(band_kernel_srf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
+      band_kernel_srf<<<(unsigned)((n + kBandThreads - 1) / kBandThreads), kBandThreads, acc_bytes, st>>>(
+          P, n, rec, ctx->d_band[sensor], ctx->d_lc, plan, nb, out, compact ? 1 : 0);
     } else if (uniform) {
       band_kernel<true><<<grid, kBandThreads, 0, st>>>(P, n, rec, ctx->d_band[sensor], nb, out, compact ? 1 : 0);
     } else {
@@ -1927,12 +2061,13 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
   const size_t elt = (flags & SPART_FLAG_F32_IO) ? sizeof(float) : sizeof(double);
   const bool compact = (flags & SPART_FLAG_COMPACT_OUT) != 0;
   const int nout = compact ? 2 : SPART_NOUT;
-  // chunks pipeline H2D / kernels / D2H over the slots.  128 Ki samples per chunk: large enough that a
-  // chunk's kernels nearly fill the GPU (1024 blocks of the band kernel; with 64 Ki the three kernels of a
-  // chunk ran at a quarter of their throughput and the pipeline became kernel-bound), small enough that
-  // the unoverlapped first H2D and last D2H stay ~10 % of a 1M batch; cap the per-slot output at ~256 MB
-  // for many-band sensors.  SPART_HOST_CHUNK overrides (tuning).
-  int64_t chunk = 1 << 17;
+  // Chunks pipeline H2D / kernels / D2H over the slots.  The bulk moves in chunks of up to 256 Ki samples
+  // (large enough that a chunk's kernels fill the GPU and that the per-copy set-up cost disappears); the first
+  // and the last chunks are small (16 Ki, doubling) because the first H2D + kernels and the last D2H overlap
+  // with nothing: measured on 1M Sentinel-2 samples, 16 equal chunks of 64 Ki gave 159 M simulations/s, equal
+  // chunks of 256 Ki 181 M/s, the ramped schedule more.  The per-slot output is capped at ~256 MB for
+  // many-band sensors.  SPART_HOST_CHUNK overrides the largest chunk (tuning).
+  int64_t chunk = 1 << 18;
   if (const char* e = getenv("SPART_HOST_CHUNK")) {
     const long long v = atoll(e);
     if (v >= 1024) chunk = v;
@@ -1940,6 +2075,20 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
   const int64_t cap_by_out = ((int64_t)256 << 20) / ((int64_t)nb * SPART_NOUT * 8);
   if (chunk > cap_by_out) chunk = cap_by_out > 1024 ? cap_by_out : 1024;
   if (chunk > n) chunk = n;
+  std::vector<int64_t> sizes;      // the chunk schedule: ramp up, bulk, ramp down
+  {
+    std::vector<int64_t> ramp;
+    int64_t rem = n;
+    for (int64_t c = 1 << 14; c < chunk && rem >= 4 * c; c *= 2) {
+      ramp.push_back(c);
+      rem -= 2 * c;
+    }
+    sizes = ramp;
+    const int64_t k = (rem + chunk - 1) / chunk;
+    int64_t each = k > 0 ? (((rem + k - 1) / k + 127) / 128) * 128 : 0;
+    for (int64_t left = rem; left > 0; left -= each) sizes.push_back(left < each ? left : each);
+    for (auto it = ramp.rbegin(); it != ramp.rend(); ++it) sizes.push_back(*it);
+  }
   // pageable caller memory is staged through pinned buffers by the copy threads (a cudaMemcpyAsync on
   // pageable memory is a synchronous single-threaded driver copy); pinned or registered memory is
   // DMA'd directly
@@ -1967,8 +2116,9 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
   };
   auto run = [&]() -> int {
     int slot = 0, prev = -1;
-    for (int64_t s0 = 0; s0 < n; s0 += chunk, slot = (slot + 1) % SpartCtx::kSlots) {
-      const int64_t m = (n - s0 < chunk) ? (n - s0) : chunk;
+    int64_t s0 = 0;
+    for (size_t ci = 0; ci < sizes.size(); s0 += sizes[ci], ++ci, slot = (slot + 1) % SpartCtx::kSlots) {
+      const int64_t m = sizes[ci];
       cudaStream_t st = ctx->streams[slot];
       int rc2 = unstage(slot);      // the slot's previous chunk (already done unless the CPU is ahead)
       if (rc2) return rc2;
