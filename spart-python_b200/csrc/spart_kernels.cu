@@ -295,6 +295,9 @@ __device__ __forceinline__ void lidf_poly_setup(double a, double b, double s, do
 #ifndef SPART_LIDF_ASTEPS
 #define SPART_LIDF_ASTEPS 2      // exact steps per bookkeeping round
 #endif
+#ifndef SPART_LIDF_A2
+#define SPART_LIDF_A2 0          // 1: stage A steps two tasks per lane side by side (ILP 2); measured 7 % SLOWER
+#endif                           // (0.620 vs 0.580 ms per 1M samples, same 62 registers), kept as a build knob
 #ifndef SPART_LIDF_BSTEPS
 #define SPART_LIDF_BSTEPS 20     // polynomial steps per bookkeeping round (best of 12..24)
 #endif
@@ -314,6 +317,101 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
   const unsigned lt_mask = (1u << lane) - 1u;
 
   // ---- stage A: exact steps ------------------------------------------------------------
+#if SPART_LIDF_A2
+  // Experiment: two tasks per lane, stepped branch-free side by side, so that the second
+  // task's dependent chain fills the first one's latency slots.  Same results bit for bit, same 62 registers,
+  // but 7 % slower on the B200 (the selects that keep finished slots frozen and the doubled hand-out
+  // bookkeeping cost more issue slots than the extra ILP recovers), so it is off by default.
+  {
+    int next = 64;                 // warp-uniform: first unassigned task; task t -> angle t / SPW, sample t % SPW
+    int task[2] = {lane, lane + 32};
+    double a[2], b[2], theta2[2], x[2], y[2];
+    bool running[2], conv[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ang = task[j] / kLidfSpw, smp = task[j] % kLidfSpw;
+      a[j] = sA[smp];
+      b[j] = sB[smp];
+      theta2[j] = c_theta2[ang];
+      x[j] = theta2[j];
+      y[j] = 0.0;
+      running[j] = true;
+      conv[j] = false;
+      if (a[j] > 1.0) {            // sailh.py:371-372: closed form F = 1 - cos(theta), no iteration
+        y[j] = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2[j])) - theta2[j]);
+        running[j] = false;
+        conv[j] = true;
+      }
+    }
+    int iters = 0;                 // warp-uniform runaway guard (non-convergent garbage input)
+    while (true) {
+#pragma unroll
+      for (int rep = 0; rep < SPART_LIDF_ASTEPS; ++rep) {
+        double s[2], c[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) sincos_small(x[j], s[j], c[j]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double yn = s[j] * fma(b[j], c[j], a[j]);                    // a sin x + b/2 sin 2x
+          const double dx = fma(0.5, yn, 0.5 * (theta2[j] - x[j]));          // (y - x + theta2) / 2
+          const double adx = fabs(dx);
+          const double yp = fma(a[j], c[j], b[j] * fma(2.0 * c[j], c[j], -1.0));   // y'(x) = a cos x + b cos 2x
+          const bool cv = !(adx > 1e-8);                                      // the reference's stop (NaN stops too)
+          const bool go = !(cv || adx <= (0.5 * SPART_LIDF_TAU) * (1.0 - yp));
+          // a lane whose task is finished keeps its values (selects, no branch: both chains stay interleaved)
+          y[j] = running[j] ? yn : y[j];
+          x[j] = running[j] ? x[j] + dx : x[j];
+          conv[j] = running[j] ? cv : conv[j];
+          running[j] = running[j] && go;
+        }
+      }
+      const unsigned idle0 = __ballot_sync(full, !running[0]);
+      const unsigned idle1 = __ballot_sync(full, !running[1]);
+      const int n0 = __popc(idle0), nidle = n0 + __popc(idle1);
+      if (next < kLidfTasks) {
+        if (nidle >= 2 * SPART_LIDF_BATCH) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (!running[j]) {
+              if (task[j] >= 0) {
+                sX[task[j]] = conv[j] ? 2.0 * y[j] + theta2[j] : x[j];
+                sDone[task[j]] = conv[j] ? 1 : 0;
+              }
+              task[j] = next + (j == 0 ? __popc(idle0 & lt_mask) : n0 + __popc(idle1 & lt_mask));
+              if (task[j] < kLidfTasks) {
+                const int ang = task[j] / kLidfSpw, smp = task[j] % kLidfSpw;
+                a[j] = sA[smp];
+                b[j] = sB[smp];
+                theta2[j] = c_theta2[ang];
+                x[j] = theta2[j];
+                running[j] = true;
+                conv[j] = false;
+                if (a[j] > 1.0) {
+                  y[j] = 0.5 * (SPART_PI * (1.0 - cos(0.5 * theta2[j])) - theta2[j]);
+                  running[j] = false;
+                  conv[j] = true;
+                }
+              } else {
+                task[j] = -1;      // nothing left for this slot
+                conv[j] = true;
+              }
+            }
+          }
+          next += nidle;
+        }
+      } else if (nidle == 64) {
+        break;
+      }
+      if (++iters > (1 << 22)) break;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (task[j] >= 0) {          // every slot ends idle with its last task's hand-over value in registers
+        sX[task[j]] = conv[j] ? 2.0 * y[j] + theta2[j] : x[j];
+        sDone[task[j]] = conv[j] ? 1 : 0;
+      }
+  }
+#else
   {
     int next = 32;                 // warp-uniform: first unassigned task; task t -> angle t / SPW, sample t % SPW
     int task = lane;
@@ -379,6 +477,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
       sDone[task] = conv ? 1 : 0;
     }
   }
+#endif
   __syncwarp();
 
   // ---- stage B: Taylor-model steps -------------------------------------------------------

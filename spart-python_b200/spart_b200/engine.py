@@ -47,11 +47,19 @@ class CompactBands:
         # the arithmetic type the kernels formed L_TOA in: float in FP32 mode, whatever the storage type
         self.fp32 = bool(fp32) or (buf.dtype in (torch.float32, np.float32))
         self.conv_ea_f64 = np.asarray(conv_ea, dtype=np.float64)
-        if isinstance(buf, torch.Tensor):
-            self.conv_ea = torch.as_tensor(self.conv_ea_f64, device=buf.device).to(
-                torch.float32 if self.fp32 else buf.dtype)
-        else:
-            self.conv_ea = self.conv_ea_f64.astype(np.float32 if self.fp32 else buf.dtype)
+        self._conv_ea = None
+
+    @property
+    def conv_ea(self):
+        """conv_ea in the arithmetic type of the run, on the buffer's device (built on first use: creating a
+        CompactBands must not touch the GPU, the gather pipeline creates one per chunk)."""
+        if self._conv_ea is None:
+            if isinstance(self.buf, torch.Tensor):
+                self._conv_ea = torch.as_tensor(self.conv_ea_f64).to(torch.float32 if self.fp32 else self.buf.dtype).to(
+                    self.buf.device)
+            else:
+                self._conv_ea = self.conv_ea_f64.astype(np.float32 if self.fp32 else self.buf.dtype)
+        return self._conv_ea
 
     @property
     def R_TOC(self):

@@ -99,7 +99,10 @@ def nearest_sharded(lut_local, obs, weights=None, group=None, index_offset=None,
     if search is None:
         _check(lut_local, obs)
         search = lambda l, o, w, off: _search(l, o, w, off, packed=True)
-    words = search(lut_local, obs, weights, index_offset)
+    if lut_local.shape[0] == 0:       # a rank without entries contributes the identity of the min-reduction
+        words = torch.full((obs.shape[0],), 2 ** 63 - 1, dtype=torch.int64, device=obs.device)
+    else:
+        words = search(lut_local, obs, weights, index_offset)
     # costs are >= 0, so the signed 64-bit order of the words is the (cost, index) order
     dist.all_reduce(words, op=dist.ReduceOp.MIN, group=group)
     return (unpack_words or unpack)(words)

@@ -19,7 +19,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 sensor = sys.argv[2] if len(sys.argv) > 2 else "Sentinel2A-MSI"
 dev = torch.device("cuda", 0)
 eng = spart_b200.default_engine(dev)
-P = bench.synthetic_params_torch(n, 123, dev)
+P = bench.synthetic_params_torch(n, 2, 123, dev)
 if len(sys.argv) > 3 and sys.argv[3] == "3":      # random geometry
     g = torch.Generator(device=dev).manual_seed(5)
     P[19] = torch.rand(n, generator=g, device=dev, dtype=torch.float64) * 65
@@ -29,12 +29,13 @@ _, st = eng.sensor(sensor)
 out = torch.empty((n, st.n_bands, 3), dtype=torch.float64, device=dev)
 precision = sys.argv[4] if len(sys.argv) > 4 else "fp64"
 uniform = not (len(sys.argv) > 3 and sys.argv[3] == "3") and os.environ.get("SPART_NO_UNIFORM") is None
+bc = bench.CONFIGS[2]["bcast"] if uniform else ()
 for _ in range(3):
-    eng.forward_bands(P, sensor, out=out, uniform_geometry=uniform, precision=precision)
+    eng.forward_bands(P, sensor, out=out, broadcast_rows=bc, precision=precision)
 torch.cuda.synchronize()
 eng.profile_enable(sensor, True)
 for _ in range(8):
-    eng.forward_bands(P, sensor, out=out, uniform_geometry=uniform, precision=precision)
+    eng.forward_bands(P, sensor, out=out, broadcast_rows=bc, precision=precision)
 torch.cuda.synchronize()
 r = eng.profile_read(sensor)
 c = r["calls"]
