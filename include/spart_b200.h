@@ -226,6 +226,13 @@ int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const fl
                       const float* weights_dev, int64_t index_offset, void* workspace_dev,
                       int64_t* best_index_dev, float* best_cost_dev, unsigned long long* packed_dev,
                       void* stream);
+/* The same search on the tensor cores (3xTF32 mma.sync over the band axis, n_bands <= 30): the entry is
+ * chosen by an approximate comparison (error ~1e-6 |obs||entry|, so near-ties may resolve differently),
+ * its reported cost is recomputed exactly in FP32.  Same arguments as spart_lut_nearest. */
+int spart_lut_nearest_tc(const float* lut_dev, int64_t n, int32_t n_bands, const float* obs_dev, int64_t m,
+                         const float* weights_dev, int64_t index_offset, void* workspace_dev,
+                         int64_t* best_index_dev, float* best_cost_dev, unsigned long long* packed_dev,
+                         void* stream);
 int spart_lut_unpack(const unsigned long long* packed_dev, int64_t m, int64_t* best_index_dev,
                      float* best_cost_dev, void* stream);
 

@@ -1159,16 +1159,17 @@ geometry_kernel_f32(const ParamsT<TIO> P, int64_t n, float* __restrict__ rec, in
   // dso (sailh.py:78) is a difference of O(1) terms that vanishes in the hot spot: a degree away from it single
   // precision has no digits left, so this one per-sample scalar is formed in FP64 from the angles as given
   float dso;
+  double us_d, uv_d, ss_d, so_d;       // cos / sin of the two zenith angles in FP64, reused by the SMAC scalars below
   {
-    double sd, cd, so_, co_, sp, cp;
-    sincos_small(tts_d * SPART_DEG2RAD, sd, cd);
-    sincos_small(tto_d * SPART_DEG2RAD, so_, co_);
+    double sp, cp;
+    sincos_small(tts_d * SPART_DEG2RAD, ss_d, us_d);
+    sincos_small(tto_d * SPART_DEG2RAD, so_d, uv_d);
     const double psi_d = fabs(rel_d - 360.0 * rint(rel_d / 360.0));
     sincos_small(psi_d * SPART_DEG2RAD, sp, cp);
     (void)sp;
-    const double ts = sd / cd, to = so_ / co_;
+    const double ts = ss_d * rcp_fast(us_d), to = so_d * rcp_fast(uv_d);
     const double d2 = ts * ts + to * to - 2.0 * ts * to * cp;
-    dso = (float)sqrt(fmax(d2, 0.0));
+    dso = (float)sqrt_fast(fmax(d2, 0.0));
   }
   const float inv_cc = SPART_PI_F * inv_cs * inv_co;
 
@@ -1242,9 +1243,8 @@ geometry_kernel_f32(const ParamsT<TIO> P, int64_t n, float* __restrict__ rec, in
 
   {
     // the scattering-angle terms keep FP64: cos(rel * 180/pi) has an argument of ~1e4 rad (smac.py:130)
-    const double us_d = cos(tts_d * SPART_DEG2RAD), uv_d = cos(tto_d * SPART_DEG2RAD);
     const double crd = 180.0 / SPART_PI;
-    double cksi = -((us_d * uv_d) + (sqrt(1.0 - us_d * us_d) * sqrt(1.0 - uv_d * uv_d) * cos(rel_d * crd)));
+    double cksi = -((us_d * uv_d) + (sqrt_fast(1.0 - us_d * us_d) * sqrt_fast(1.0 - uv_d * uv_d) * cos(rel_d * crd)));
     if (cksi < -1.0) cksi = -1.0;
     const float us = (float)us_d, uv = (float)uv_d;
     const float Peq = (float)(P.at(P_PA, s) / 1013.25);
@@ -2036,6 +2036,60 @@ int spart_lut_nearest(const float* lut_dev, int64_t n, int32_t n_bands, const fl
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   if (best_index_dev && best_cost_dev && !packed_dev) {
+    lut_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(best, m, best_index_dev, best_cost_dev);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return SPART_OK;
+}
+
+int spart_lut_nearest_tc(const float* lut_dev, int64_t n, int32_t n_bands, const float* obs_dev, int64_t m,
+                         const float* weights_dev, int64_t index_offset, void* workspace_dev, int64_t* best_index_dev,
+                         float* best_cost_dev, unsigned long long* packed_dev, void* stream) {
+  if (!lut_dev || !obs_dev || (!workspace_dev && m > 0))
+    return fail(SPART_EINVAL, "spart_lut_nearest_tc: null argument%s");
+  if (!packed_dev && (!best_index_dev || !best_cost_dev))
+    return fail(SPART_EINVAL, "spart_lut_nearest_tc: need best_index_dev + best_cost_dev or packed_dev%s");
+  if (n <= 0 || n > 0x7fffffffLL || m < 0 || n_bands < 1 || n_bands > 30 || index_offset < 0 ||
+      index_offset + n > 0xffffffffLL)
+    return fail(SPART_EINVAL,
+                "spart_lut_nearest_tc: need 1 <= n < 2^31, m >= 0, 1 <= n_bands <= 30, index_offset + n < 2^32%s");
+  if (m == 0) return SPART_OK;
+  NvtxRange r("spart::lut_nearest_tc");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* best = packed_dev ? packed_dev : (unsigned long long*)workspace_dev;
+  CUDA_TRY(cudaMemsetAsync(best, 0xff, sizeof(unsigned long long) * m, st));
+  int dev = 0, sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int ks = (n_bands + 2 + 7) / 8;                 // bands + the two |l|^2 slots, in k-steps of 8
+  const int obs_per_block = kTcWarps * 16 * (ks <= 2 ? 4 : 2);
+  const int64_t obs_blocks = (m + obs_per_block - 1) / obs_per_block;
+  int64_t slices = (8LL * sms + obs_blocks - 1) / obs_blocks;
+  const int64_t max_slices = (n + kTcTile - 1) / kTcTile;
+  if (slices > max_slices) slices = max_slices;
+  if (slices > 65535) slices = 65535;
+  if (slices < 1) slices = 1;
+  int64_t per_slice = (n + slices - 1) / slices;
+  per_slice = ((per_slice + kTcTile - 1) / kTcTile) * kTcTile;
+  slices = (n + per_slice - 1) / per_slice;
+  dim3 grid((unsigned)obs_blocks, (unsigned)slices);
+  const unsigned off = (unsigned)index_offset;
+  if (ks <= 2)
+    lut_nearest_tc_kernel<2, 4><<<grid, kTcWarps * 32, 0, st>>>(lut_dev, n, n_bands, obs_dev, m, weights_dev, per_slice,
+                                                               off, best);
+  else if (ks == 3)
+    lut_nearest_tc_kernel<3, 2><<<grid, kTcWarps * 32, 0, st>>>(lut_dev, n, n_bands, obs_dev, m, weights_dev, per_slice,
+                                                               off, best);
+  else
+    lut_nearest_tc_kernel<4, 2><<<grid, kTcWarps * 32, 0, st>>>(lut_dev, n, n_bands, obs_dev, m, weights_dev, per_slice,
+                                                               off, best);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  lut_refine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(lut_dev, n_bands, obs_dev, m, weights_dev, off, best);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  if (!packed_dev) {
     lut_unpack_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(best, m, best_index_dev, best_cost_dev);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());

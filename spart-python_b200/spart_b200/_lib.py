@@ -30,7 +30,7 @@ FP32 = 32
 EXPORTS = (
     "spart_abi_version", "spart_last_error", "spart_device_count", "spart_create", "spart_destroy",
     "spart_workspace_bytes", "spart_forward_bands", "spart_forward_bands_host", "spart_forward_spectrum",
-    "spart_smac", "spart_sailh", "spart_lut_workspace_bytes", "spart_lut_nearest", "spart_lut_unpack",
+    "spart_smac", "spart_sailh", "spart_lut_workspace_bytes", "spart_lut_nearest", "spart_lut_nearest_tc", "spart_lut_unpack",
     "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
 )
 
@@ -90,6 +90,7 @@ def load():
     lib.spart_lut_workspace_bytes.restype = c_size_t
     lib.spart_lut_nearest.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_int64, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.spart_lut_nearest_tc.argtypes = lib.spart_lut_nearest.argtypes
     lib.spart_lut_unpack.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]

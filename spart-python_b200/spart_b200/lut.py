@@ -39,10 +39,14 @@ def _check(lut, obs):
         raise ValueError("lut [n, nb] and obs [m, nb] must be CUDA float32 tensors with the same band count")
 
 
-def _search(lut, obs, weights, index_offset, packed):
-    """spart_lut_nearest on the current stream.  packed=True: returns the int64 words
+def _search(lut, obs, weights, index_offset, packed, method="exact"):
+    """spart_lut_nearest (method="exact": FP32 SIMT) or spart_lut_nearest_tc (method="tensor": 3xTF32 tensor-core
+    search + exact re-costing of the winner) on the current stream.  packed=True: returns the int64 words
     (cost bits << 32 | global index) instead of (index, cost)."""
+    if method not in ("exact", "tensor"):
+        raise ValueError("method must be 'exact' or 'tensor'")
     lib = _lib.load()
+    fn = lib.spart_lut_nearest if method == "exact" else lib.spart_lut_nearest_tc
     lut, obs = lut.contiguous(), obs.contiguous()
     n, nb = lut.shape
     m = obs.shape[0]
@@ -55,7 +59,7 @@ def _search(lut, obs, weights, index_offset, packed):
     cost = None if packed else torch.empty(m, dtype=torch.float32, device=lut.device)
     with torch.cuda.device(lut.device):
         stream = torch.cuda.current_stream(lut.device).cuda_stream
-        _lib.check(lib.spart_lut_nearest(lut.data_ptr(), n, nb, obs.data_ptr(), m, 0 if w is None else w.data_ptr(),
+        _lib.check(fn(lut.data_ptr(), n, nb, obs.data_ptr(), m, 0 if w is None else w.data_ptr(),
                                          int(index_offset), ws.data_ptr(), 0 if packed else idx.data_ptr(),
                                          0 if packed else cost.data_ptr(), words.data_ptr() if packed else 0,
                                          stream), "spart_lut_nearest")
@@ -75,14 +79,17 @@ def unpack(words):
     return idx, cost
 
 
-def nearest(lut, obs, weights=None):
+def nearest(lut, obs, weights=None, method="exact"):
     """lut: CUDA float32 [n, nb]; obs: CUDA float32 [m, nb]; weights: optional per-band weights [nb].
-    Returns (index int64 [m], cost float32 [m]) of the entry minimising sum_b w_b (obs_b - lut_b)^2."""
+    Returns (index int64 [m], cost float32 [m]) of the entry minimising sum_b w_b (obs_b - lut_b)^2.
+    method="tensor": the comparison runs on the tensor cores in 3xTF32 (the entry is optimal up to ~1e-6 of
+    |obs||entry|, its cost is exact)."""
     _check(lut, obs)
-    return _search(lut, obs, weights, 0, packed=False)
+    return _search(lut, obs, weights, 0, packed=False, method=method)
 
 
-def nearest_sharded(lut_local, obs, weights=None, group=None, index_offset=None, search=None, unpack_words=None):
+def nearest_sharded(lut_local, obs, weights=None, group=None, index_offset=None, search=None, unpack_words=None,
+                    method="exact"):
     """Retrieval against a table that stays sharded over the ranks of `group` (each rank holds
     `lut_local` [n_r, nb], rank order = table order; every rank passes the same `obs`).  Each GPU
     searches its own slice, the per-observation words (cost bits << 32 | global index) are
@@ -98,7 +105,7 @@ def nearest_sharded(lut_local, obs, weights=None, group=None, index_offset=None,
             raise ValueError("nearest_sharded: the table has 2^32 entries or more")
     if search is None:
         _check(lut_local, obs)
-        search = lambda l, o, w, off: _search(l, o, w, off, packed=True)
+        search = lambda l, o, w, off: _search(l, o, w, off, packed=True, method=method)
     if lut_local.shape[0] == 0:       # a rank without entries contributes the identity of the min-reduction
         words = torch.full((obs.shape[0],), 2 ** 63 - 1, dtype=torch.int64, device=obs.device)
     else:

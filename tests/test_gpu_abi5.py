@@ -240,3 +240,32 @@ def test_sharded_lut_single_rank_pieces(env):
     w1 = lut._search(L[20_000:], O, None, 20_000, packed=True)
     i2, c2 = lut.unpack(torch.minimum(w0, w1))
     assert torch.equal(i2, idx) and torch.equal(c2, cost)
+
+
+@pytest.mark.parametrize("nb,n,m", [(13, 50_000, 3000), (26, 20_000, 1000), (6, 4000, 777), (1, 300, 33), (20, 9999, 257)])
+def test_lut_tensor_core_search(env, nb, n, m):
+    """method="tensor" (3xTF32 mma.sync search + exact re-costing): the chosen entry is optimal up to the
+    3xTF32 comparison error, the reported cost is the exact FP32 cost of that entry, self-matches are found."""
+    torch, sb, so = env
+    from spart_b200 import lut
+    g = torch.Generator(device="cuda").manual_seed(nb)
+    L = torch.rand((n, nb), generator=g, device="cuda", dtype=torch.float32)
+    O = torch.rand((m, nb), generator=g, device="cuda", dtype=torch.float32)
+    w = torch.rand(nb, generator=g, device="cuda", dtype=torch.float32) + 0.1
+    for weights in (None, w):
+        idx, cost = lut.nearest(L, O, weights, method="tensor")
+        ie, ce = lut.nearest(L, O, weights)
+        ww = torch.ones(nb, device="cuda") if weights is None else weights
+        d = ((O[:, None, :].double() - L[None, :, :].double()) ** 2 * ww.double()).sum(-1)
+        chosen = d.gather(1, idx[:, None])[:, 0]
+        scale = ((O.double() ** 2 * ww.double()).sum(-1).sqrt()[:, None] * (L.double() ** 2 * ww.double()).sum(-1).sqrt()[None, :]).max()
+        assert torch.all(chosen <= d.min(dim=1).values + 4e-6 * scale)
+        assert torch.allclose(cost.double(), chosen, rtol=1e-4, atol=1e-9)          # the cost is that entry's exact cost
+        assert (idx == ie).float().mean() > (0.999 if m >= 1000 else 0.9)     # near-ties may resolve differently
+    idx, cost = lut.nearest(L, L[100:164].clone(), method="tensor")
+    assert torch.equal(idx.cpu(), torch.arange(100, 164)) and float(cost.max()) == 0.0
+    w0 = lut._search(L[:n // 3], O, None, 0, packed=True, method="tensor")
+    w1 = lut._search(L[n // 3:], O, None, n // 3, packed=True, method="tensor")
+    i2, c2 = lut.unpack(torch.minimum(w0, w1))
+    i1, c1 = lut.nearest(L, O, method="tensor")
+    assert torch.equal(c2, c1)

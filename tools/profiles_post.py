@@ -96,7 +96,7 @@ def main(tag):
         h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
         hdr = rows[h]
         keep = ["ID", "Kernel Name", "Grid Size", "Block Size", "Metric Name", "Metric Unit", "Metric Value"]
-        dur = {}
+        dur = {}          # (kernel, grid) -> durations; the full-batch launches are those with the largest grid
         with open(prof / f"{tag}_launches.csv", "w", newline="") as f:
             w = csv.writer(f)
             w.writerow(keep)
@@ -106,8 +106,16 @@ def main(tag):
                 d = dict(zip(hdr, r))
                 d["Kernel Name"] = ncu_summary.base_name(d["Kernel Name"])
                 w.writerow([d[k] for k in keep])
-                dur.setdefault(d["Kernel Name"], []).append(float(d["Metric Value"].replace(",", "")))
-        fp64 = {k: sum(v[-2:]) / 2 for k, v in dur.items() if k in bench.KERNELS}      # the last (timed) steps
+                blocks = 1
+                for x in re.findall(r"\d+", d["Grid Size"]):
+                    blocks *= int(x)
+                dur.setdefault((d["Kernel Name"], blocks), []).append(float(d["Metric Value"].replace(",", "")))
+        fp64 = {}
+        for k in bench.KERNELS:
+            grids = [g for (kk, g) in dur if kk == k]
+            if grids:
+                v = dur[(k, max(grids))]
+                fp64[k] = sum(v) / len(v)
         tot = sum(fp64.values())
         print("ncu launch-list shares:", {k: round(v / tot, 3) for k, v in fp64.items()})
         km = line["roofline"]["kernel_ms"]
