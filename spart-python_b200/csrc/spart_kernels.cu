@@ -3,8 +3,9 @@
 // Data flow for one batch (all buffers in HBM, struct-of-arrays over samples so that every
 // warp-wide access is one or two fully used 128-byte lines):
 //
-//   params [27][n]  --lidf_kernel---->  ws rows F_1..F_12 [12][n]   (warp = task queue over
-//        64 samples x 12 angles: the reference's truncated leaf-angle iteration, step for step)
+//   params [27][n]  --lidf_kernel------>  ws rows F_1..F_12 [12][n]   (block = 128 samples x 12 angles: the
+//        reference's truncated leaf-angle iteration, step for step, run as groups of 32 tasks sorted by
+//        predicted step count; lidf_kernel_v1 is the round-1 warp-queue version, kept behind SPART_LIDF_V2=0)
 //   params + F      --geometry_kernel-> rec [R_COUNT][n]   (one thread per sample: 13-class volume
 //        scattering, hot-spot integrals, soil vector weights, SMAC geometry/pressure scalars, ET scale)
 //   params + rec    --band_kernel---->  out [n][nb][3]      (one thread per sample, looping over a
@@ -217,6 +218,9 @@ constexpr int kSampleThreads = 128;
 // internal launch flag (not part of the ABI): rows 19..21 are broadcast rows, i.e. the batch shares one
 // sun / observer geometry by construction
 constexpr int kFlagUniform = 1;
+// internal launch flag: LIDFa and LIDFb are broadcast rows, the twelve F values were computed once (element 0)
+constexpr int kFlagLidfBcast = 1 << 30;
+constexpr uint32_t kLidfRows = (1u << P_LIDFA) | (1u << P_LIDFB);
 constexpr uint32_t kGeometryRows = (1u << P_SZA) | (1u << P_VZA) | (1u << P_RAA);
 
 // Leaf inclination distribution for the 32 samples of a warp (sailh.py:351-398).
@@ -583,7 +587,7 @@ constexpr int kLidfThreads = SPART_LIDF_THREADS;
 // ab0/ab1: the LIDFa / LIDFb rows with element strides st0/st1 (1, or 0 for a broadcast row);
 // F(theta_i) of sample s is written to out[i * stride_ang + s * stride_smp].
 __global__ void __launch_bounds__(kLidfThreads, SPART_LIDF_MINBLOCKS)
-lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t st0, int64_t st1, int64_t n,
+lidf_kernel_v1(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t st0, int64_t st1, int64_t n,
             double* __restrict__ out, int64_t stride_ang, int64_t stride_smp) {
   constexpr int kWarps = kLidfThreads / 32;
   __shared__ double sA[kWarps][kLidfSpw], sB[kWarps][kLidfSpw];
@@ -603,7 +607,7 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
 }
 
 // ---- leaf-angle kernel, version 2: the same iterations, scheduled as length-sorted groups ----------------
-// lidf_kernel above treats a warp's (sample, angle) tasks as a queue; with task lengths of 1..26 exact and
+// lidf_kernel_v1 above treats a warp's (sample, angle) tasks as a queue; with task lengths of 1..26 exact and
 // 3..84 polynomial steps (mean 4.3 / 19.9 on the benchmark distribution) its lanes spend ~45 % of the issued
 // instructions in rounds they have already finished or in divergent hand-out code (tools/lidf_queue_sim.py).
 // Version 2 runs exactly the same arithmetic per task -- results are bit-identical -- but orders the work by
@@ -628,13 +632,16 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
 #define SPART_LIDF2_RA 1
 #endif
 #ifndef SPART_LIDF2_CENTRED
-#define SPART_LIDF2_CENTRED 1    // 0: hand over at TAU and expand around the hand-over iterate (bit-identical to lidf_kernel)
+#define SPART_LIDF2_CENTRED 1    // 0: hand over at TAU and expand around the hand-over iterate (bit-identical to lidf_kernel_v1)
 #endif
 #ifndef SPART_LIDF2_R
 #define SPART_LIDF2_R 0.15       // hand-over radius of the centred Taylor model
 #endif
 #ifndef SPART_LIDF2_AB_SMEM
 #define SPART_LIDF2_AB_SMEM 1    // 0: stages A2 / B re-read LIDFa / LIDFb from global memory (2 KB less shared memory)
+#endif
+#ifndef SPART_LIDF2_BILP
+#define SPART_LIDF2_BILP 1       // groups a warp steps side by side in stage B
 #endif
 #ifndef SPART_LIDF2_SKIP
 #define SPART_LIDF2_SKIP 0       // timing experiments only: 1 = stop after A1 + sort, 2 = stop after A2 + sort
@@ -681,7 +688,7 @@ __device__ __forceinline__ float lidf2_lg2(float x) {
 
 // Hand-over test of an exact step at x with step dx and slope yp = y'(x).
 // SPART_LIDF2_CENTRED = 0: the Newton estimate 2 |dx| / (1 - y') of the distance to the fixed point is below TAU
-//   (the rule of lidf_kernel; stage B expands around the next iterate).
+//   (the rule of lidf_kernel_v1; stage B expands around the next iterate).
 // SPART_LIDF2_CENTRED = 1: stage B expands around the Newton estimate xc = x + 2 dx / (1 - y') of the fixed point
 //   itself.  The truncation error c |x_n - xc|^7 of the degree-6 model is then largest for the first
 //   polynomial iterates, where it matters least: the iteration contracts an error made at distance d from the
@@ -791,7 +798,7 @@ __device__ __forceinline__ void lidf2_sort(Lidf2Smem& S, BinFn binfn, int idle) 
 }
 
 __global__ void __launch_bounds__(kL2Threads, SPART_LIDF2_MINBLOCKS)
-lidf2_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t st0, int64_t st1, int64_t n,
+lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int64_t st0, int64_t st1, int64_t n,
              double* __restrict__ out, int64_t stride_ang, int64_t stride_smp) {
   __shared__ Lidf2Smem S;
   const unsigned full = 0xffffffffu;
@@ -800,7 +807,7 @@ lidf2_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int
   if (tid < 12) {
     const double th = c_theta2[tid];
     double s, c;
-    sincos_small(th, s, c);          // the values the first exact step of lidf_kernel computes
+    sincos_small(th, s, c);          // the values the first exact step of lidf_kernel_v1 computes
     S.theta2[tid] = th;
     S.sin0[tid] = s;
     S.cos0[tid] = c;
@@ -892,54 +899,71 @@ lidf2_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int
   lidf2_sort(S, [](unsigned char v) { return 63 - (int)(v & 63); }, 63);   // 63 .. 1 polynomial steps -> bins 0 .. 62
 
   // ---- B: Taylor-model steps ---------------------------------------------------------------------------
+  // A warp takes SPART_LIDF2_BILP consecutive groups (neighbours in the sorted order, so of about the same length)
+  // and steps them side by side: the Horner chains of the groups interleave and fill each other's latency slots.
   if (SPART_LIDF2_SKIP == 0) {
+    constexpr int NG = SPART_LIDF2_BILP;
     const int nwork = S.nwork;
     while (true) {
       int g = 0;
-      if (lane == 0) g = atomicAdd(&S.counter, 1);
+      if (lane == 0) g = atomicAdd(&S.counter, NG);
       g = __shfl_sync(full, g, 0);
       if (g * 32 >= nwork) break;
-      const int pos = g * 32 + lane;
-      const bool has = pos < nwork;
-      const int t = S.perm[has ? pos : 0];
-      const int ang = t / kL2Samples, smp = t % kL2Samples;
-      const double theta2 = S.theta2[ang];
-      const double xs = S.x[t];
+      bool has[NG];
+      int t[NG];
+      double theta2[NG], k0[NG], u[NG], gk[NG][kLidfDeg + 1];
+#pragma unroll
+      for (int j = 0; j < NG; ++j) {
+        const int pos = (g + j) * 32 + lane;
+        has[j] = pos < nwork;
+        t[j] = S.perm[has[j] ? pos : 0];
+        const int ang = t[j] / kL2Samples, smp = t[j] % kL2Samples;
+        theta2[j] = S.theta2[ang];
+        const double xs = S.x[t[j]];
 #if SPART_LIDF2_CENTRED
-      const double xc = xs + (double)S.dq[t] * (1.0 / 256.0);     // expansion centre: near the fixed point
-      double u = xs - xc;                                           // (exact)
+        const double xc = xs + (double)S.dq[t[j]] * (1.0 / 256.0);   // expansion centre: near the fixed point
+        u[j] = xs - xc;                                               // (exact)
 #else
-      const double xc = xs;
-      double u = 0.0;
+        const double xc = xs;
+        u[j] = 0.0;
 #endif
-      double gk[kLidfDeg + 1];
-      double s, c;
-      sincos_small(xc, s, c);
-      const double k0 = theta2 - xc;
+        double s, c;
+        sincos_small(xc, s, c);
+        k0[j] = theta2[j] - xc;
 #if SPART_LIDF2_CENTRED
-      lidf2_poly_setup(LIDF2_A(smp), LIDF2_B(smp), s, c, k0, gk);
+        lidf2_poly_setup(LIDF2_A(smp), LIDF2_B(smp), s, c, k0[j], gk[j]);
 #else
-      lidf_poly_setup(LIDF2_A(smp), LIDF2_B(smp), s, c, k0, gk);      // bit-identical to lidf_kernel
+        lidf_poly_setup(LIDF2_A(smp), LIDF2_B(smp), s, c, k0[j], gk[j]);      // bit-identical to lidf_kernel_v1
 #endif
-      bool running = has;
+      }
+      bool running = false;
       int iters = 0;
       do {
         // a lane stays on the iterate u from which its first step with |du| <= 1e-8 starts: from then on it
         // repeats that step, so no separate "finished" state is carried through the steps
 #pragma unroll
         for (int rep = 0; rep < SPART_LIDF2_RB; ++rep) {
-          const double un = lidf_poly(gk, u);
-          running = fabs(un - u) > 1e-8;          // the reference's stop (NaN stops too)
-          u = running ? un : u;
+          double un[NG];
+#pragma unroll
+          for (int j = 0; j < NG; ++j) un[j] = lidf_poly(gk[j], u[j]);
+          running = false;
+#pragma unroll
+          for (int j = 0; j < NG; ++j) {
+            const bool r = fabs(un[j] - u[j]) > 1e-8;     // the reference's stop (NaN stops too)
+            u[j] = r ? un[j] : u[j];
+            running = running || (r && has[j]);
+          }
         }
-      } while (__any_sync(full, running && has) && ++iters < (1 << 22));
-      if (has) {
-        // y~(u) = 2 g(u) - u - k0, so 2 y + theta2 = 4 g(u) - 2 u - 2 k0 + theta2 at the last iterate
-        const double uf = u;
-        const double unf = lidf_poly(gk, uf);
-        S.x[t] = (2.0 * (2.0 * unf - uf - k0) + theta2) * (1.0 / SPART_PI);
-        S.key[t] = 1;
-      }
+      } while (__any_sync(full, running) && ++iters < (1 << 22));
+#pragma unroll
+      for (int j = 0; j < NG; ++j)
+        if (has[j]) {
+          // y~(u) = 2 g(u) - u - k0, so 2 y + theta2 = 4 g(u) - 2 u - 2 k0 + theta2 at the last iterate
+          const double uf = u[j];
+          const double unf = lidf_poly(gk[j], uf);
+          S.x[t[j]] = (2.0 * (2.0 * unf - uf - k0[j]) + theta2[j]) * (1.0 / SPART_PI);
+          S.key[t[j]] = 1;
+        }
     }
   }
   __syncthreads();
@@ -995,10 +1019,11 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
   }
   // uniform geometry: the twelve F loads are issued here, so that their latency overlaps the
   // volume-scattering classes computed by 13 threads of the block
+  const int64_t sF = (flags & kFlagLidfBcast) ? 0 : s;      // one leaf-angle distribution for the whole batch
   double F[12];
   if (uniform_geometry) {
 #pragma unroll
-    for (int i = 0; i < 12; ++i) F[i] = rec[(size_t)(kRowF + i) * n + s];
+    for (int i = 0; i < 12; ++i) F[i] = rec[(size_t)(kRowF + i) * n + sF];
   }
   const double psi = fabs(rel - 360.0 * rint(rel / 360.0));
   const double psi_rad = psi * SPART_DEG2RAD;
@@ -1044,11 +1069,11 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
     }
   } else {
     double Fprev = 0.0;
-    double Fnext = rec[(size_t)kRowF * n + s];
+    double Fnext = rec[(size_t)kRowF * n + sF];
 #pragma unroll 1
     for (int i = 0; i < 13; ++i) {
       const double Fi = (i < 12) ? Fnext : 1.0;
-      if (i < 11) Fnext = rec[(size_t)(kRowF + i + 1) * n + s];   // in flight during volscatt_class
+      if (i < 11) Fnext = rec[(size_t)(kRowF + i + 1) * n + sF];   // in flight during volscatt_class
       const double lidf = Fi - Fprev;
       Fprev = Fi;
       double chi_s, chi_o, frho, ftau;
@@ -2079,18 +2104,21 @@ size_t spart_workspace_bytes(const SpartCtx* ctx, int64_t n) {
   return sizeof(double) * (size_t)kWsRows * (size_t)n;
 }
 
-static int launch_lidf(const Params& P, int64_t n, double* ws, cudaStream_t st) {
+static int launch_lidf(const Params& P, int64_t n_batch, double* ws, cudaStream_t st) {
+  // LIDFa and LIDFb both broadcast rows (a look-up table with one leaf-angle distribution): the twelve
+  // iterations run once, geometry_kernel reads element 0 of the F rows (kFlagLidfBcast)
+  const int64_t n = ((P.bc & kLidfRows) == kLidfRows) ? 1 : n_batch;
 #if SPART_LIDF_V2
   const unsigned blocks = (unsigned)((n + kL2Samples - 1) / kL2Samples);
-  lidf2_kernel<<<blocks, kL2Threads, 0, st>>>(P.p + P_LIDFA * P.ld, P.p + P_LIDFB * P.ld,
+  lidf_kernel<<<blocks, kL2Threads, 0, st>>>(P.p + P_LIDFA * P.ld, P.p + P_LIDFB * P.ld,
                                                 ((P.bc >> P_LIDFA) & 1u) ? 0 : 1, ((P.bc >> P_LIDFB) & 1u) ? 0 : 1, n,
-                                                ws + (size_t)kRowF * n, n, 1);
+                                                ws + (size_t)kRowF * n_batch, n_batch, 1);
 #else
   const int64_t per_block = (int64_t)(kLidfThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel<<<blocks, kLidfThreads, 0, st>>>(P.p + P_LIDFA * P.ld, P.p + P_LIDFB * P.ld,
+  lidf_kernel_v1<<<blocks, kLidfThreads, 0, st>>>(P.p + P_LIDFA * P.ld, P.p + P_LIDFB * P.ld,
                                                  ((P.bc >> P_LIDFA) & 1u) ? 0 : 1, ((P.bc >> P_LIDFB) & 1u) ? 0 : 1, n,
-                                                 ws + (size_t)kRowF * n, n, 1);
+                                                 ws + (size_t)kRowF * n_batch, n_batch, 1);
 #endif
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -2099,6 +2127,7 @@ static int launch_lidf(const Params& P, int64_t n, double* ws, cudaStream_t st) 
 
 static int launch_geometry(const Params& P, int64_t n, double* ws, int kflags, cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+  if ((P.bc & kLidfRows) == kLidfRows) kflags |= kFlagLidfBcast;
   geometry_kernel<<<blocks, kSampleThreads, 0, st>>>(P, n, ws, kflags);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -2479,12 +2508,12 @@ int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_de
   }
   NvtxRange r("spart::leaf_angles");
 #if SPART_LIDF_V2
-  lidf2_kernel<<<(unsigned)((n + kL2Samples - 1) / kL2Samples), kL2Threads, 0, (cudaStream_t)stream>>>(
+  lidf_kernel<<<(unsigned)((n + kL2Samples - 1) / kL2Samples), kL2Threads, 0, (cudaStream_t)stream>>>(
       ab_dev, ab_dev + ld, 1, 1, n, out_dev, 1, 13);
 #else
   const int64_t per_block = (int64_t)(kLidfThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel<<<blocks, kLidfThreads, 0, (cudaStream_t)stream>>>(ab_dev, ab_dev + ld, 1, 1, n, out_dev, 1, 13);
+  lidf_kernel_v1<<<blocks, kLidfThreads, 0, (cudaStream_t)stream>>>(ab_dev, ab_dev + ld, 1, 1, n, out_dev, 1, 13);
 #endif
   ++g_launches;
   CUDA_TRY(cudaGetLastError());

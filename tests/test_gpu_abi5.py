@@ -68,6 +68,24 @@ def test_broadcast_rows_equal_full_rows(env):
     assert np.array_equal(got32, sb.run_batch_params(_dev(torch, P), "LANDSAT8-OLI", precision="fp32").cpu().numpy())
     with pytest.raises(ValueError):
         sb.run_batch_params(dev, "LANDSAT8-OLI", broadcast_rows=[27])
+    # LIDFa and LIDFb both broadcast: the leaf-angle iterations run once for the batch (also with a shared
+    # geometry); only one of them broadcast: the general path
+    P[:, so.SZA], P[:, so.VZA], P[:, so.RAA] = 33.0, 7.0, 40.0
+    full = sb.run_batch_params(_dev(torch, P), "Sentinel2A-MSI").cpu().numpy()
+    for rows in ([so.LIDFA, so.LIDFB, so.SZA, so.VZA, so.RAA], [so.LIDFA, so.SZA, so.VZA, so.RAA], [so.LIDFB]):
+        Q = P.copy()
+        Q[1:, rows] = np.nan
+        got = sb.run_batch_params(_dev(torch, Q), "Sentinel2A-MSI", broadcast_rows=rows).cpu().numpy()
+        if so.SZA in rows:      # the folded-geometry kernels re-associate a few sums
+            assert relerr(got, full) < 1e-12
+        else:
+            assert np.array_equal(got, full)
+    a = sb.run_batch_params(_dev(torch, P), "Sentinel2A-MSI", broadcast_rows=[so.SZA, so.VZA, so.RAA]).cpu().numpy()
+    Q = P.copy()
+    Q[1:, [so.LIDFA, so.LIDFB]] = np.nan
+    b = sb.run_batch_params(_dev(torch, Q), "Sentinel2A-MSI",
+                            broadcast_rows=[so.LIDFA, so.LIDFB, so.SZA, so.VZA, so.RAA]).cpu().numpy()
+    assert np.array_equal(a, b)
 
 
 def test_uniform_geometry_is_validated(env):
