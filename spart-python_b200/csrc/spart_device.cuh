@@ -688,9 +688,11 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   const double Cs = cos_ttli * cos_tts, Ss = sin_ttli * sin_tts;
   const double Co = cos_ttli * cos_tto, So = sin_ttli * sin_tto;
   const double As = fmax(Ss, Cs), Ao = fmax(So, Co);
-  // true divisions: the quotient is exactly -1 whenever Cs >= Ss (As == Cs), and acos amplifies a
-  // 1-ulp deviation from -1 to 1e-8
-  const double zs = -Cs / As, zo = -Co / Ao;
+  // the quotient is exactly -1 whenever Cs >= Ss (As == Cs) -- acos amplifies a 1-ulp deviation from -1 to
+  // 1e-8, so that case is a select; otherwise -Cs / Ss comes from the fast reciprocal (<= 1 ulp; chi_s, chi_o are
+  // stationary in bts, bto there, and the reference's own correctly rounded quotient is as ill-conditioned)
+  const double zs = (Cs >= Ss) ? -1.0 : -Cs * rcp_fast(Ss);
+  const double zo = (Co >= So) ? -1.0 : -Co * rcp_fast(So);
   const double bts = acos(zs), bto = acos(zo);
   // sin(acos z) = sqrt(1 - z^2) (>= 0 on [0, pi]); differs from sin of the rounded angle by < 2e-16 absolute
   const double sbts = sqrt_fast(fma(-zs, zs, 1.0)), sbto = sqrt_fast(fma(-zo, zo, 1.0));

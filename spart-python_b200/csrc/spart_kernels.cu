@@ -943,9 +943,21 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
         // repeats that step, so no separate "finished" state is carried through the steps
 #pragma unroll
         for (int rep = 0; rep < SPART_LIDF2_RB; ++rep) {
+          // the Horner chains of the NG groups advance together, term by term: independent FP64 instructions
+          // issued back to back by one warp keep the pipe's 2-cycle cadence, whereas FP64 instructions of
+          // different warps follow each other every 3 cycles (tools/micro/fp64_latency.cu)
           double un[NG];
 #pragma unroll
-          for (int j = 0; j < NG; ++j) un[j] = lidf_poly(gk[j], u[j]);
+          for (int j = 0; j < NG; ++j) un[j] = gk[j][kLidfDeg];
+#pragma unroll
+          for (int k = kLidfDeg - 1; k >= 0; --k)
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+              if (NG > 1)     // volatile: keeps the term-by-term order through the compiler's own scheduling
+                asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(un[j]) : "d"(un[j]), "d"(u[j]), "d"(gk[j][k]));
+              else
+                un[j] = fma(un[j], u[j], gk[j][k]);
+            }
           running = false;
 #pragma unroll
           for (int j = 0; j < NG; ++j) {

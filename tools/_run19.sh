@@ -1,0 +1,2 @@
+python tools/kbench.py 1000000 LANDSAT8-OLI 3 | tail -1
+python -m pytest tests -m gpu -q -x 2>&1 | tail -4
