@@ -1006,6 +1006,24 @@ __global__ void lidf_diff_kernel(double* __restrict__ out, int64_t n) {
   }
 }
 
+// SMAC scalars that depend on the sun / observer angles only (smac.py:98-102, 125-141), in the order
+// m, ln m, cksi, ksiD, Rayleigh phase, 1/(1+us), 1/(1+uv), us uv/(us+uv)
+__device__ __forceinline__ void smac_angle_scalars(double us, double uv, double inv_us, double inv_uv, double rel,
+                                                   double* o) {
+  const double crd = 180.0 / SPART_PI;
+  double cksi = -((us * uv) + (sqrt(1.0 - us * us) * sqrt(1.0 - uv * uv) * cos(rel * crd)));
+  if (cksi < -1.0) cksi = -1.0;
+  const double m = inv_us + inv_uv;
+  o[0] = m;
+  o[1] = log_fast(m);
+  o[2] = cksi;
+  o[3] = crd * acos(cksi);
+  o[4] = 0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742;
+  o[5] = rcp_fast(1.0 + us);
+  o[6] = rcp_fast(1.0 + uv);
+  o[7] = us * uv * rcp_fast(us + uv);
+}
+
 // Kernel 2, one thread per sample: everything else that does not depend on wavelength or
 // band.  With uniform_geometry != 0 all samples share sun/observer angles (a look-up table
 // for one acquisition geometry): the 13-class volume-scattering terms are then evaluated
@@ -1037,32 +1055,58 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
 #pragma unroll
     for (int i = 0; i < 12; ++i) F[i] = rec[(size_t)(kRowF + i) * n + sF];
   }
-  const double psi = fabs(rel - 360.0 * rint(rel / 360.0));
-  const double psi_rad = psi * SPART_DEG2RAD;
-  // zenith angles and the folded azimuth are a few radians at most: bounded-range sincos
-  double sin_tts, cos_tts, sin_tto, cos_tto, sin_psi, cos_psi;
-  sincos_small(tts * SPART_DEG2RAD, sin_tts, cos_tts);
-  sincos_small(tto * SPART_DEG2RAD, sin_tto, cos_tto);
-  sincos_small(psi_rad, sin_psi, cos_psi);
-  const double inv_cs = rcp_fast(cos_tts), inv_co = rcp_fast(cos_tto);
-  const double inv_cc = SPART_PI * inv_cs * inv_co;
-  const double tan_tts = sin_tts * inv_cs, tan_tto = sin_tto * inv_co;
-  // like the reference, a rounding-negative radicand gives NaN (sailh.py:78)
-  const double dso = sqrt_fast(tan_tts * tan_tts + tan_tto * tan_tto - 2.0 * tan_tts * tan_tto * cos_psi);
-
-  if (uniform_geometry) {
-    if (tid < 13) {
-      double chi_s, chi_o, frho, ftau;
-      volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, sin_psi, cos_psi, c_sin_ttli[tid], c_cos_ttli[tid], chi_s,
-                     chi_o, frho, ftau);
-      s_cls[tid][0] = chi_s * inv_cs;
-      s_cls[tid][1] = chi_o * inv_co;
-      s_cls[tid][2] = frho * inv_cc;
-      s_cls[tid][3] = ftau * inv_cc;
+  // Scalars that depend on the sun / observer angles only (sailh.py:59-78, smac.py:98-102, 129-141).  With a
+  // shared geometry they are the same for every sample: warp 0 computes them (its lanes 0..12 also evaluate the
+  // volume-scattering classes) and lane 13 publishes them through shared memory -- the other warps skip three
+  // sincos, a cos, an acos, a logarithm and six reciprocals per sample.
+  enum { GS_COS_TTS, GS_COS_TTO, GS_INV_CS, GS_INV_CO, GS_DSO, GS_M, GS_LM, GS_CKSI, GS_KSID, GS_RAYPH, GS_INV1PUS,
+         GS_INV1PUV, GS_AA3, GS_COUNT };
+  __shared__ double s_gs[GS_COUNT];
+  double gs[GS_COUNT];     // (only GS_COS_TTS .. GS_DSO stay live in the per-sample path)
+  double sin_tts = 0.0, sin_tto = 0.0, psi_rad = 0.0, sin_psi = 0.0, cos_psi = 0.0;   // (per-class path below)
+  if (!uniform_geometry || tid < 32) {
+    const double psi = fabs(rel - 360.0 * rint(rel / 360.0));
+    psi_rad = psi * SPART_DEG2RAD;
+    // zenith angles and the folded azimuth are a few radians at most: bounded-range sincos
+    double cos_tts, cos_tto;
+    sincos_small(tts * SPART_DEG2RAD, sin_tts, cos_tts);
+    sincos_small(tto * SPART_DEG2RAD, sin_tto, cos_tto);
+    sincos_small(psi_rad, sin_psi, cos_psi);
+    const double inv_cs = rcp_fast(cos_tts), inv_co = rcp_fast(cos_tto);
+    const double tan_tts = sin_tts * inv_cs, tan_tto = sin_tto * inv_co;
+    gs[GS_COS_TTS] = cos_tts;
+    gs[GS_COS_TTO] = cos_tto;
+    gs[GS_INV_CS] = inv_cs;
+    gs[GS_INV_CO] = inv_co;
+    // like the reference, a rounding-negative radicand gives NaN (sailh.py:78)
+    gs[GS_DSO] = sqrt_fast(tan_tts * tan_tts + tan_tto * tan_tto - 2.0 * tan_tts * tan_tto * cos_psi);
+    if (uniform_geometry) {
+      smac_angle_scalars(cos_tts, cos_tto, inv_cs, inv_co, rel, &gs[GS_M]);
+      if (tid < 13) {
+        const double inv_cc = SPART_PI * inv_cs * inv_co;
+        double chi_s, chi_o, frho, ftau;
+        volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, sin_psi, cos_psi, c_sin_ttli[tid], c_cos_ttli[tid],
+                       chi_s, chi_o, frho, ftau);
+        s_cls[tid][0] = chi_s * inv_cs;
+        s_cls[tid][1] = chi_o * inv_co;
+        s_cls[tid][2] = frho * inv_cc;
+        s_cls[tid][3] = ftau * inv_cc;
+      }
+      if (tid == 13) {
+#pragma unroll
+        for (int i = 0; i < GS_COUNT; ++i) s_gs[i] = gs[i];
+      }
     }
   }
   __syncthreads();
   if (!valid) return;
+  if (uniform_geometry) {
+#pragma unroll
+    for (int i = 0; i <= GS_DSO; ++i) gs[i] = s_gs[i];
+  }
+  const double cos_tts = gs[GS_COS_TTS], cos_tto = gs[GS_COS_TTO], inv_cs = gs[GS_INV_CS], inv_co = gs[GS_INV_CO];
+  const double dso = gs[GS_DSO];
+  const double inv_cc = SPART_PI * inv_cs * inv_co;
 
   // 13 leaf-inclination classes, dotted with lidf (sailh.py:81-97)
   double k = 0.0, K = 0.0, bf = 0.0, sob = 0.0, sof = 0.0;
@@ -1131,31 +1175,33 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
     rec[R_EMU * n + s] = exp_fast(-mu);
   }
 
-  // SMAC per-sample scalars (smac.py:98-102, 129-141)
+  // SMAC per-sample scalars (smac.py:98-102, 129-141); the angle-only ones were formed above
   {
     const double us = cos_tts, uv = cos_tto;    // cos(tts*cdr), cos(tto*cdr)
     const double Peq = P.at(P_PA, s) * (1.0 / 1013.25);
-    const double m = inv_cs + inv_co;
-    const double crd = 180.0 / SPART_PI;
-    double cksi = -((us * uv) + (sqrt(1.0 - us * us) * sqrt(1.0 - uv * uv) * cos(rel * crd)));
-    if (cksi < -1.0) cksi = -1.0;
-    const double ksiD = crd * acos(cksi);
+    if (uniform_geometry) {
+#pragma unroll
+      for (int i = GS_M; i < GS_COUNT; ++i) gs[i] = s_gs[i];
+    } else {
+      smac_angle_scalars(cos_tts, cos_tto, inv_cs, inv_co, rel, &gs[GS_M]);
+    }
+    const double m = gs[GS_M];
     rec[R_US * n + s] = us;
     rec[R_UV * n + s] = uv;
     rec[R_M * n + s] = m;
     rec[R_PEQ * n + s] = Peq;
     rec[R_LO3 * n + s] = log_fast(P.at(P_UO3, s) * m);
     rec[R_LH2O * n + s] = log_fast(P.at(P_UH2O, s) * m);
-    rec[R_LM * n + s] = log_fast(m);
+    rec[R_LM * n + s] = gs[GS_LM];
     rec[R_LPEQ * n + s] = log_fast(Peq);
-    rec[R_CKSI * n + s] = cksi;
-    rec[R_KSID * n + s] = ksiD;
-    rec[R_RAYPH * n + s] = 0.7190443 * (1.0 + (cksi * cksi)) + 0.0412742;
+    rec[R_CKSI * n + s] = gs[GS_CKSI];
+    rec[R_KSID * n + s] = gs[GS_KSID];
+    rec[R_RAYPH * n + s] = gs[GS_RAYPH];
     rec[R_INVUS * n + s] = inv_cs;
     rec[R_INVUV * n + s] = inv_co;
-    rec[R_INV1PUS * n + s] = rcp_fast(1.0 + us);
-    rec[R_INV1PUV * n + s] = rcp_fast(1.0 + uv);
-    rec[R_AA3 * n + s] = us * uv * rcp_fast(us + uv);
+    rec[R_INV1PUS * n + s] = gs[GS_INV1PUS];
+    rec[R_INV1PUV * n + s] = gs[GS_INV1PUV];
+    rec[R_AA3 * n + s] = gs[GS_AA3];
     // extraterrestrial radiance scale (SPART.py:345-353)
     const double b = 2.0 * SPART_PI * P.at(P_DOY, s) * (1.0 / 365.0);
     double sb, cb, s2b, c2b;
