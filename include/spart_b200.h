@@ -164,9 +164,12 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_
                         int32_t flags, void* workspace_dev, void* out_dev, void* stream);
 
 /* Same computation with HOST buffers: params_host [SPART_NPAR][ld] and out_host (layout and
- * element type as above, SPART_OUT_ELEMS elements) are ordinary host memory.  The batch is cut
- * into chunks of 128 Ki samples that are pipelined over four internal streams (H2D, kernels,
- * D2H).  Pinned or registered buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are
+ * element type as above, SPART_OUT_ELEMS elements) are ordinary host memory.  The parameters travel
+ * in spans of up to 128 Ki samples (one 2-D copy per run of per-sample rows) into three device
+ * buffers; each span is evaluated in place in chunks of up to 64 Ki samples whose results flow back
+ * as they complete.  One stream per copy direction, one per output slot, tied by events, so both
+ * copy engines and the SMs run side by side.  Pinned or registered buffers (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory) are
  * DMA'd directly; pageable buffers (plain NumPy arrays) are staged through internal pinned
  * buffers by a small pool of copy threads (SPART_HOST_THREADS, default 8), because an asynchronous
  * copy on pageable memory degenerates to a synchronous single-threaded driver copy.  Broadcast

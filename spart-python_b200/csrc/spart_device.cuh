@@ -94,13 +94,19 @@ __constant__ double c_glp_w[SPART_NQ2] = SPART_GL16_W;
 // A parameter batch as the kernels see it: [P_COUNT][ld] of T (double; float with SPART_FLAG_F32_IO).
 // Rows whose bit is set in `bc` are constant over the batch ("broadcast rows"): only their element 0
 // is ever read, which all lanes load from the same address.
+// `pb` is the base the broadcast rows are read from: the same as `p` for a caller's batch; the host-buffer path
+// evaluates chunks of a larger device-resident span (p = span + chunk offset) whose broadcast elements sit at the
+// start of the span's rows (pb = span).
 template <typename T>
 struct ParamsT {
   const T* p;
   int64_t ld;
   uint32_t bc;
-  __device__ __forceinline__ const T* ptr(int row, int64_t s) const {
-    return p + row * ld + (((bc >> row) & 1u) ? 0 : s);
+  const T* pb;
+  __host__ __device__ ParamsT(const T* p_, int64_t ld_, uint32_t bc_, const T* pb_ = nullptr)
+      : p(p_), ld(ld_), bc(bc_), pb(pb_ ? pb_ : p_) {}
+  __host__ __device__ __forceinline__ const T* ptr(int row, int64_t s) const {
+    return ((bc >> row) & 1u) ? pb + row * ld : p + row * ld + s;
   }
   __device__ __forceinline__ T at(int row, int64_t s) const { return __ldg(ptr(row, s)); }
 };

@@ -193,8 +193,18 @@ struct SpartCtx {
   std::mutex mu;
   static const int kSlots = 4;
   cudaStream_t streams[kSlots] = {};
-  cudaEvent_t slot_done[kSlots] = {};
-  void* slot_params[kSlots] = {};
+  cudaEvent_t slot_done[kSlots] = {};      // the slot's device->host copy has finished
+  cudaEvent_t slot_k[kSlots] = {};         // the slot's kernels have finished
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // one stream per copy direction (see the host path)
+  cudaStream_t join_stream = nullptr;
+  static const int kInSlots = 3;           // device buffers for the parameter spans of the host path
+  void* in_params[kInSlots] = {};
+  cudaEvent_t in_done[kInSlots] = {};      // the span's host->device copies have finished
+  cudaEvent_t in_free[kInSlots] = {};      // the kernels of all chunks of the span have finished
+  int64_t in_cap = 0;                      // samples per span buffer
+  void* bc_stage = nullptr;                // pinned: element 0 of the broadcast rows of the current call
+  void* in_ets[kInSlots] = {};             // compact output: the span's etscale values, sent back once per span
+  cudaEvent_t ets_done[kInSlots] = {};
   double* slot_rec[kSlots] = {};
   void* slot_out[kSlots] = {};
   void* stage_in[kSlots] = {};     // pinned host
@@ -1963,14 +1973,25 @@ int spart_destroy(SpartCtx* ctx) {
   DeviceGuard guard(ctx->device);
   for (int i = 0; i < SpartCtx::kSlots; ++i) {
     if (ctx->streams[i]) cudaStreamSynchronize(ctx->streams[i]);
-    if (ctx->slot_params[i]) cudaFree(ctx->slot_params[i]);
     if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
     if (ctx->slot_out[i]) cudaFree(ctx->slot_out[i]);
     if (ctx->stage_in[i]) cudaFreeHost(ctx->stage_in[i]);
     if (ctx->stage_out[i]) cudaFreeHost(ctx->stage_out[i]);
     if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
+    if (ctx->slot_k[i]) cudaEventDestroy(ctx->slot_k[i]);
     if (ctx->streams[i]) cudaStreamDestroy(ctx->streams[i]);
   }
+  for (int i = 0; i < SpartCtx::kInSlots; ++i) {
+    if (ctx->in_params[i]) cudaFree(ctx->in_params[i]);
+    if (ctx->in_done[i]) cudaEventDestroy(ctx->in_done[i]);
+    if (ctx->in_free[i]) cudaEventDestroy(ctx->in_free[i]);
+    if (ctx->in_ets[i]) cudaFree(ctx->in_ets[i]);
+    if (ctx->ets_done[i]) cudaEventDestroy(ctx->ets_done[i]);
+  }
+  if (ctx->bc_stage) cudaFreeHost(ctx->bc_stage);
+  if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+  if (ctx->join_stream) cudaStreamDestroy(ctx->join_stream);
   delete ctx->pool;
   for (auto& pe : ctx->prof_pending) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
   for (auto& pe : ctx->prof_free) for (int i = 0; i < 4; ++i) cudaEventDestroy(pe.e[i]);
@@ -2168,13 +2189,13 @@ static int launch_lidf(const Params& P, int64_t n_batch, double* ws, cudaStream_
   const int64_t n = ((P.bc & kLidfRows) == kLidfRows) ? 1 : n_batch;
 #if SPART_LIDF_V2
   const unsigned blocks = (unsigned)((n + kL2Samples - 1) / kL2Samples);
-  lidf_kernel<<<blocks, kL2Threads, 0, st>>>(P.p + P_LIDFA * P.ld, P.p + P_LIDFB * P.ld,
+  lidf_kernel<<<blocks, kL2Threads, 0, st>>>(P.ptr(P_LIDFA, 0), P.ptr(P_LIDFB, 0),
                                                 ((P.bc >> P_LIDFA) & 1u) ? 0 : 1, ((P.bc >> P_LIDFB) & 1u) ? 0 : 1, n,
                                                 ws + (size_t)kRowF * n_batch, n_batch, 1);
 #else
   const int64_t per_block = (int64_t)(kLidfThreads / 32) * kLidfSpw;
   const unsigned blocks = (unsigned)((n + per_block - 1) / per_block);
-  lidf_kernel_v1<<<blocks, kLidfThreads, 0, st>>>(P.p + P_LIDFA * P.ld, P.p + P_LIDFB * P.ld,
+  lidf_kernel_v1<<<blocks, kLidfThreads, 0, st>>>(P.ptr(P_LIDFA, 0), P.ptr(P_LIDFB, 0),
                                                  ((P.bc >> P_LIDFA) & 1u) ? 0 : 1, ((P.bc >> P_LIDFB) & 1u) ? 0 : 1, n,
                                                  ws + (size_t)kRowF * n_batch, n_batch, 1);
 #endif
@@ -2223,10 +2244,10 @@ static int check_mode(const SpartCtx* ctx, int32_t sensor, int32_t precision, in
 }  // extern "C"
 
 template <typename TIO>
-static int launch_fp32(const SpartCtx* ctx, int sensor, const void* params_dev, int64_t n, int64_t ld, uint32_t bc,
-                       int kflags, bool reuse, bool compact, float* rec, void* out_dev, dim3 grid, cudaStream_t st,
-                       bool prof, const SpartCtx::ProfEvents& pe) {
-  const ParamsT<TIO> P{(const TIO*)params_dev, ld, bc};
+static int launch_fp32(const SpartCtx* ctx, int sensor, const void* params_dev, const void* params_bc_dev, int64_t n,
+                       int64_t ld, uint32_t bc, int kflags, bool reuse, bool compact, float* rec, void* out_dev,
+                       dim3 grid, cudaStream_t st, bool prof, const SpartCtx::ProfEvents& pe) {
+  const ParamsT<TIO> P{(const TIO*)params_dev, ld, bc, (const TIO*)params_bc_dev};
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[1], st));
   if (!reuse) {
     NvtxRange r("spart::geometry_f32");
@@ -2242,11 +2263,11 @@ static int launch_fp32(const SpartCtx* ctx, int sensor, const void* params_dev, 
   return SPART_OK;
 }
 
-extern "C" {
-
-int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_dev, int64_t n, int64_t ld,
-                        uint32_t broadcast_rows, int32_t precision, int32_t flags, void* workspace_dev, void* out_dev,
-                        void* stream) {
+// spart_forward_bands with a separate base for the broadcast rows (see ParamsT); the host-buffer path calls it on
+// chunks of a device-resident span
+static int forward_bands_impl(const SpartCtx* ctx, int32_t sensor, const void* params_dev, const void* params_bc_dev,
+                              int64_t n, int64_t ld, uint32_t broadcast_rows, int32_t precision, int32_t flags,
+                              void* workspace_dev, void* out_dev, void* stream) {
   int rc = check_batch(ctx, params_dev, n, ld, broadcast_rows, workspace_dev, out_dev, "spart_forward_bands");
   if (rc) return rc;
   rc = check_mode(ctx, sensor, precision, flags, "spart_forward_bands");
@@ -2278,7 +2299,7 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_
   const int kflags = (flags & SPART_FLAG_SOIL_SPECTRUM) | (uniform ? kFlagUniform : 0);
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
   if (precision == SPART_FP64) {
-    const Params P{(const double*)params_dev, ld, broadcast_rows};
+    const Params P{(const double*)params_dev, ld, broadcast_rows, (const double*)params_bc_dev};
     double* out = (double*)out_dev;
     if (!reuse) {
       NvtxRange r("spart::leaf_angles");
@@ -2309,10 +2330,10 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_
     }
   } else {   // SPART_FP32: the leaf angles are solved inside the geometry kernel
     if (flags & SPART_FLAG_F32_IO)
-      rc = launch_fp32<float>(ctx, sensor, params_dev, n, ld, broadcast_rows, kflags, reuse, compact, (float*)rec,
+      rc = launch_fp32<float>(ctx, sensor, params_dev, params_bc_dev, n, ld, broadcast_rows, kflags, reuse, compact, (float*)rec,
                               out_dev, grid, st, prof, pe);
     else
-      rc = launch_fp32<double>(ctx, sensor, params_dev, n, ld, broadcast_rows, kflags, reuse, compact, (float*)rec,
+      rc = launch_fp32<double>(ctx, sensor, params_dev, params_bc_dev, n, ld, broadcast_rows, kflags, reuse, compact, (float*)rec,
                                out_dev, grid, st, prof, pe);
     if (rc) return rc;
   }
@@ -2324,6 +2345,15 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_
     ctx->prof_pending.push_back(pe);
   }
   return SPART_OK;
+}
+
+extern "C" {
+
+int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_dev, int64_t n, int64_t ld,
+                        uint32_t broadcast_rows, int32_t precision, int32_t flags, void* workspace_dev, void* out_dev,
+                        void* stream) {
+  return forward_bands_impl(ctx, sensor, params_dev, params_dev, n, ld, broadcast_rows, precision, flags,
+                            workspace_dev, out_dev, stream);
 }
 
 int spart_profile_enable(SpartCtx* ctx, int32_t on) {
@@ -2591,18 +2621,23 @@ static bool is_pinned_host(const void* p) {
   return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-static int ensure_slots(SpartCtx* ctx, int64_t chunk, size_t out_bytes, bool stage_in, bool stage_out) {
-  const size_t in_bytes = sizeof(double) * P_COUNT * (size_t)chunk;
+// buffers, streams and events of the host path: kInSlots parameter spans of `span` samples, kSlots record /
+// output slots of `chunk` samples, pinned staging buffers for pageable caller memory
+static int ensure_slots(SpartCtx* ctx, int64_t span, int64_t chunk, size_t out_bytes, bool stage_in, bool stage_out) {
+  const size_t in_bytes = sizeof(double) * P_COUNT * (size_t)span;
+  cudaStream_t* extra[3] = {&ctx->h2d_stream, &ctx->d2h_stream, &ctx->join_stream};
+  for (cudaStream_t* e : extra) {
+    if (!*e) CUDA_TRY(cudaStreamCreateWithFlags(e, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamSynchronize(*e));
+  }
   for (int i = 0; i < SpartCtx::kSlots; ++i) {
     if (!ctx->streams[i]) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->streams[i], cudaStreamNonBlocking));
     if (!ctx->slot_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
+    if (!ctx->slot_k[i]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->slot_k[i], cudaEventDisableTiming));
     CUDA_TRY(cudaStreamSynchronize(ctx->streams[i]));
     if (ctx->slot_cap < chunk) {
-      if (ctx->slot_params[i]) cudaFree(ctx->slot_params[i]);
       if (ctx->slot_rec[i]) cudaFree(ctx->slot_rec[i]);
-      ctx->slot_params[i] = nullptr;
       ctx->slot_rec[i] = nullptr;
-      CUDA_TRY(cudaMalloc(&ctx->slot_params[i], in_bytes));
       CUDA_TRY(cudaMalloc(&ctx->slot_rec[i], sizeof(double) * kWsRows * chunk));
     }
     if (ctx->slot_out_cap < out_bytes) {
@@ -2610,18 +2645,33 @@ static int ensure_slots(SpartCtx* ctx, int64_t chunk, size_t out_bytes, bool sta
       ctx->slot_out[i] = nullptr;
       CUDA_TRY(cudaMalloc(&ctx->slot_out[i], out_bytes));
     }
-    if (stage_in && ctx->stage_in_cap < in_bytes) {
-      if (ctx->stage_in[i]) cudaFreeHost(ctx->stage_in[i]);
-      ctx->stage_in[i] = nullptr;
-      CUDA_TRY(cudaHostAlloc(&ctx->stage_in[i], in_bytes, cudaHostAllocDefault));
-    }
     if (stage_out && ctx->stage_out_cap < out_bytes) {
       if (ctx->stage_out[i]) cudaFreeHost(ctx->stage_out[i]);
       ctx->stage_out[i] = nullptr;
       CUDA_TRY(cudaHostAlloc(&ctx->stage_out[i], out_bytes, cudaHostAllocDefault));
     }
   }
+  if (!ctx->bc_stage) CUDA_TRY(cudaHostAlloc(&ctx->bc_stage, sizeof(double) * P_COUNT, cudaHostAllocDefault));
+  for (int i = 0; i < SpartCtx::kInSlots; ++i) {
+    if (!ctx->in_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->in_done[i], cudaEventDisableTiming));
+    if (!ctx->in_free[i]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->in_free[i], cudaEventDisableTiming));
+    if (!ctx->ets_done[i]) CUDA_TRY(cudaEventCreateWithFlags(&ctx->ets_done[i], cudaEventDisableTiming));
+    if (ctx->in_cap < span) {
+      if (ctx->in_params[i]) cudaFree(ctx->in_params[i]);
+      if (ctx->in_ets[i]) cudaFree(ctx->in_ets[i]);
+      ctx->in_params[i] = nullptr;
+      ctx->in_ets[i] = nullptr;
+      CUDA_TRY(cudaMalloc(&ctx->in_params[i], in_bytes));
+      CUDA_TRY(cudaMalloc(&ctx->in_ets[i], sizeof(double) * (size_t)span));
+    }
+    if (stage_in && ctx->stage_in_cap < in_bytes) {
+      if (ctx->stage_in[i]) cudaFreeHost(ctx->stage_in[i]);
+      ctx->stage_in[i] = nullptr;
+      CUDA_TRY(cudaHostAlloc(&ctx->stage_in[i], in_bytes, cudaHostAllocDefault));
+    }
+  }
   if (ctx->slot_cap < chunk) ctx->slot_cap = chunk;
+  if (ctx->in_cap < span) ctx->in_cap = span;
   if (ctx->slot_out_cap < out_bytes) ctx->slot_out_cap = out_bytes;
   if (stage_in && ctx->stage_in_cap < in_bytes) ctx->stage_in_cap = in_bytes;
   if (stage_out && ctx->stage_out_cap < out_bytes) ctx->stage_out_cap = out_bytes;
@@ -2664,116 +2714,221 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
   const size_t elt = (flags & SPART_FLAG_F32_IO) ? sizeof(float) : sizeof(double);
   const bool compact = (flags & SPART_FLAG_COMPACT_OUT) != 0;
   const int nout = compact ? 2 : SPART_NOUT;
-  // Chunks pipeline H2D / kernels / D2H over the slots.  The bulk moves in chunks of up to 256 Ki samples
-  // (large enough that a chunk's kernels fill the GPU and that the per-copy set-up cost disappears); the first
-  // and the last chunks are small (16 Ki, doubling) because the first H2D + kernels and the last D2H overlap
-  // with nothing: measured on 1M Sentinel-2 samples, 16 equal chunks of 64 Ki gave 159 M simulations/s, equal
-  // chunks of 256 Ki 181 M/s, the ramped schedule more.  The per-slot output is capped at ~256 MB for
-  // many-band sensors.  SPART_HOST_CHUNK overrides the largest chunk (tuning).
-  int64_t chunk = 1 << 18;
+  // The pipeline has two granularities.
+  //   Spans (up to 128 Ki samples) are the unit of the host->device copy: one 2-D copy per run of rows into one of
+  //   kInSlots device buffers.  A host->device copy issued next to a saturated device->host stream pays ~40 us
+  //   of latency per copy operation on this box, so few, large operations matter (SPART_HOST_TRACE timeline).
+  //   Chunks (up to 64 Ki samples) are the unit of the kernels and of the device->host copy: a span's chunks are
+  //   evaluated in place (params = span + offset, broadcast rows from the span's first elements, see ParamsT),
+  //   so results start to flow back after the first chunk, not after the first span.
+  // Streams: ONE per copy direction (each slot's own stream first carried its copies too: the host->device copy of
+  // a later chunk then queued behind the device->host copy of an earlier one), one compute stream per output
+  // slot and a join stream, tied together by events:
+  //   H2D(span j)  waits until the kernels of every chunk of span j - kInSlots have finished (join stream)
+  //   kernels(i)   wait for H2D(span of i) and for D2H(i - kSlots)   (the slot's output buffer is free)
+  //   D2H(i)       waits for kernels(i)
+  // The first spans are small (32 Ki, 96 Ki samples) and the last chunk is split down to 16 Ki, because the first
+  // H2D + kernels and the last D2H overlap with nothing.  SPART_HOST_SPAN / SPART_HOST_CHUNK override the sizes.
+  int64_t span_max = 1 << 17, chunk = 1 << 16;      // best of {96, 128, 192, 256} Ki x {32, 48, 64, 128} Ki on 1M samples
+  if (const char* e = getenv("SPART_HOST_SPAN")) {
+    const long long v = atoll(e);
+    if (v >= 1024) span_max = v;
+  }
   if (const char* e = getenv("SPART_HOST_CHUNK")) {
     const long long v = atoll(e);
     if (v >= 1024) chunk = v;
   }
-  const int64_t cap_by_out = ((int64_t)256 << 20) / ((int64_t)nb * SPART_NOUT * 8);
+  const int64_t cap_by_out = ((int64_t)256 << 20) / ((int64_t)nb * SPART_NOUT * 8);   // <= ~256 MB of output per slot
   if (chunk > cap_by_out) chunk = cap_by_out > 1024 ? cap_by_out : 1024;
+  chunk = (chunk / 128) * 128;
+  if (span_max < chunk) span_max = chunk;
+  span_max = (span_max / chunk) * chunk;
   if (chunk > n) chunk = n;
-  std::vector<int64_t> sizes;      // the chunk schedule: ramp up, bulk, ramp down
+  if (span_max > n) span_max = n;
+  struct Span { int64_t s0, m; };
+  std::vector<Span> spans;
   {
-    std::vector<int64_t> ramp;
-    int64_t rem = n;
-    for (int64_t c = 1 << 14; c < chunk && rem >= 4 * c; c *= 2) {
-      ramp.push_back(c);
-      rem -= 2 * c;
+    int64_t s0 = 0;
+    for (int64_t c = (1 << 15); c < span_max && n - s0 >= 4 * c; c *= 3) {     // 32 Ki, 96 Ki
+      const int64_t m = (c / 128) * 128;
+      spans.push_back({s0, m});
+      s0 += m;
     }
-    sizes = ramp;
-    const int64_t k = (rem + chunk - 1) / chunk;
-    int64_t each = k > 0 ? (((rem + k - 1) / k + 127) / 128) * 128 : 0;
-    for (int64_t left = rem; left > 0; left -= each) sizes.push_back(left < each ? left : each);
-    for (auto it = ramp.rbegin(); it != ramp.rend(); ++it) sizes.push_back(*it);
+    while (s0 < n) {
+      const int64_t m = (n - s0 < span_max) ? n - s0 : span_max;
+      spans.push_back({s0, m});
+      s0 += m;
+    }
   }
   // pageable caller memory is staged through pinned buffers by the copy threads (a cudaMemcpyAsync on
   // pageable memory is a synchronous single-threaded driver copy); pinned or registered memory is
   // DMA'd directly
   const bool stage_in = !is_pinned_host(params_host), stage_out = !is_pinned_host(out_host);
   const size_t out_chunk_bytes = ((size_t)chunk * nb * nout + (compact ? (size_t)chunk : 0)) * elt;
-  rc = ensure_slots(ctx, chunk, out_chunk_bytes, stage_in, stage_out);
+  rc = ensure_slots(ctx, span_max, chunk, out_chunk_bytes, stage_in, stage_out);
   if (rc) return rc;
   const char* pin = (const char*)params_host;
   char* pout = (char*)out_host;
   char* pets = pout + (size_t)n * nb * 2 * elt;      // compact output: etscale[n] follows [n][nb][2]
 
   struct Pending { int64_t s0 = 0, m = 0; bool live = false; } pend[SpartCtx::kSlots];
-  // wait for a slot's chunk (its staging buffers may then be reused) and, with a pageable output,
-  // copy the chunk from the pinned staging buffer into the caller's array
+  // SPART_HOST_TRACE=1 (tuning aid): CUDA events per span and per chunk, printed as a timeline when the call ends
+  const bool trace = getenv("SPART_HOST_TRACE") != nullptr;
+  struct TraceEv { cudaEvent_t e[2]; int64_t m; int slot; bool span; };
+  std::vector<TraceEv> tev;
+  cudaEvent_t trace_t0 = nullptr;
+  if (trace) {
+    cudaEventCreate(&trace_t0);
+    cudaEventRecord(trace_t0, ctx->h2d_stream);
+  }
+  auto trace_new = [&](int64_t m, int slot, bool span) {
+    if (!trace) return;
+    TraceEv t;
+    for (auto& e : t.e) cudaEventCreate(&e);
+    t.m = m;
+    t.slot = slot;
+    t.span = span;
+    tev.push_back(t);
+  };
+  auto mark = [&](int which, cudaStream_t st) {
+    if (trace) cudaEventRecord(tev.back().e[which], st);
+  };
+  // wait for a slot's chunk and, with a pageable output, copy it from the pinned staging buffer into the
+  // caller's array (the staging buffer may then be reused)
   auto unstage = [&](int slot) -> int {
     Pending& q = pend[slot];
     if (!q.live) return SPART_OK;
     q.live = false;
     CUDA_TRY(cudaEventSynchronize(ctx->slot_done[slot]));
-    if (!stage_out) return SPART_OK;
     const size_t main_bytes = (size_t)q.m * nb * nout * elt;
     pool_memcpy(ctx->pool, pout + (size_t)q.s0 * nb * nout * elt, ctx->stage_out[slot], main_bytes);
     if (compact) memcpy(pets + (size_t)q.s0 * elt, (char*)ctx->stage_out[slot] + main_bytes, (size_t)q.m * elt);
     return SPART_OK;
   };
   auto run = [&]() -> int {
+    cudaStream_t sin = ctx->h2d_stream, sout = ctx->d2h_stream, sjoin = ctx->join_stream;
+    bool in_used[SpartCtx::kInSlots] = {}, used[SpartCtx::kSlots] = {};
     int slot = 0, prev = -1;
-    int64_t s0 = 0;
-    for (size_t ci = 0; ci < sizes.size(); s0 += sizes[ci], ++ci, slot = (slot + 1) % SpartCtx::kSlots) {
-      const int64_t m = sizes[ci];
-      cudaStream_t st = ctx->streams[slot];
-      int rc2 = unstage(slot);      // the slot's previous chunk (already done unless the CPU is ahead)
-      if (rc2) return rc2;
-      // parameter rows: ld apart on the host, m apart in the slot; a broadcast row moves one element
+    // The rows of a span buffer are ctx->in_cap elements apart whatever the span's length, so the broadcast
+    // elements have fixed places: they go in once per call and buffer, while the link is still idle (a tiny copy
+    // issued later, next to a saturated device->host stream, costs as much as 2 MB of payload).
+    const int64_t dld = ctx->in_cap;
+    if (broadcast_rows) {
+      for (int r = 0; r < P_COUNT; ++r)
+        if ((broadcast_rows >> r) & 1u) memcpy((char*)ctx->bc_stage + (size_t)r * elt, pin + (size_t)r * ld * elt, elt);
+      for (int i = 0; i < SpartCtx::kInSlots && i < (int)spans.size(); ++i)
+        for (int r0 = 0; r0 < P_COUNT;) {
+          if (!((broadcast_rows >> r0) & 1u)) {
+            ++r0;
+            continue;
+          }
+          int r1 = r0 + 1;
+          while (r1 < P_COUNT && ((broadcast_rows >> r1) & 1u)) ++r1;
+          CUDA_TRY(cudaMemcpy2DAsync((char*)ctx->in_params[i] + (size_t)r0 * dld * elt, (size_t)dld * elt,
+                                     (char*)ctx->bc_stage + (size_t)r0 * elt, elt, elt, r1 - r0,
+                                     cudaMemcpyHostToDevice, sin));
+          r0 = r1;
+        }
+    }
+    // compact result in pinned memory: the etscale values travel once per span instead of once per chunk
+    const bool ets_per_span = compact && !stage_out;
+    const bool single_compute = getenv("SPART_HOST_MULTI_COMPUTE") == nullptr;
+    for (size_t j = 0; j < spans.size(); ++j) {
+      const int islot = (int)(j % SpartCtx::kInSlots);
+      const int64_t sp0 = spans[j].s0, sm = spans[j].m;
+      // ---- host -> device: the span's parameter rows (ld apart on the host, sm apart on the device; a
+      // broadcast row moves one element)
       const char* src = pin;
       size_t src_pitch = (size_t)ld * elt;
-      size_t src_off = (size_t)s0 * elt;
+      size_t src_off = (size_t)sp0 * elt;
       if (stage_in) {
-        char* stg = (char*)ctx->stage_in[slot];
+        if (in_used[islot]) CUDA_TRY(cudaEventSynchronize(ctx->in_done[islot]));   // the staging buffer has been read
+        char* stg = (char*)ctx->stage_in[islot];
         ctx->pool->parallel_for(P_COUNT, [&](int r) {
-          const bool bc = (broadcast_rows >> r) & 1u;
-          memcpy(stg + (size_t)r * m * elt, pin + (size_t)r * ld * elt + (bc ? 0 : (size_t)s0 * elt),
-                 bc ? elt : (size_t)m * elt);
+          if (!((broadcast_rows >> r) & 1u))
+            memcpy(stg + (size_t)r * sm * elt, pin + (size_t)r * ld * elt + (size_t)sp0 * elt, (size_t)sm * elt);
         });
         src = stg;
-        src_pitch = (size_t)m * elt;
+        src_pitch = (size_t)sm * elt;
         src_off = 0;
       }
-      for (int r0 = 0; r0 < P_COUNT;) {     // runs of rows of the same kind become one 2-D copy
-        const bool bc = (broadcast_rows >> r0) & 1u;
+      if (in_used[islot]) CUDA_TRY(cudaStreamWaitEvent(sin, ctx->in_free[islot], 0));
+      trace_new(sm, islot, true);
+      mark(0, sin);
+      for (int r0 = 0; r0 < P_COUNT;) {     // runs of per-sample rows become one 2-D copy each
+        if ((broadcast_rows >> r0) & 1u) {
+          ++r0;
+          continue;
+        }
         int r1 = r0 + 1;
-        while (r1 < P_COUNT && (((broadcast_rows >> r1) & 1u) != 0) == bc) ++r1;
-        const size_t off = (bc && !stage_in) ? 0 : src_off;
-        CUDA_TRY(cudaMemcpy2DAsync((char*)ctx->slot_params[slot] + (size_t)r0 * m * elt, (size_t)m * elt,
-                                   src + (size_t)r0 * src_pitch + off, src_pitch, bc ? elt : (size_t)m * elt,
-                                   r1 - r0, cudaMemcpyHostToDevice, st));
+        while (r1 < P_COUNT && !((broadcast_rows >> r1) & 1u)) ++r1;
+        CUDA_TRY(cudaMemcpy2DAsync((char*)ctx->in_params[islot] + (size_t)r0 * dld * elt, (size_t)dld * elt,
+                                   src + (size_t)r0 * src_pitch + src_off, src_pitch, (size_t)sm * elt, r1 - r0,
+                                   cudaMemcpyHostToDevice, sin));
         r0 = r1;
       }
-      rc2 = spart_forward_bands(ctx, sensor, ctx->slot_params[slot], m, m, broadcast_rows, precision, flags,
-                                ctx->slot_rec[slot], ctx->slot_out[slot], st);
-      if (rc2) return rc2;
-      const size_t main_bytes = (size_t)m * nb * nout * elt;
-      if (stage_out) {
-        CUDA_TRY(cudaMemcpyAsync(ctx->stage_out[slot], ctx->slot_out[slot], main_bytes + (compact ? m * elt : 0),
-                                 cudaMemcpyDeviceToHost, st));
-      } else {
-        CUDA_TRY(cudaMemcpyAsync(pout + (size_t)s0 * nb * nout * elt, ctx->slot_out[slot], main_bytes,
-                                 cudaMemcpyDeviceToHost, st));
-        if (compact)
-          CUDA_TRY(cudaMemcpyAsync(pets + (size_t)s0 * elt, (char*)ctx->slot_out[slot] + main_bytes, (size_t)m * elt,
-                                   cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(ctx->in_done[islot], sin));
+      mark(1, sin);
+      in_used[islot] = true;
+      // ---- the span's chunks: kernels in place, device -> host
+      std::vector<int64_t> sizes;
+      for (int64_t left = sm; left > 0;) {
+        int64_t m = left < chunk ? left : chunk;
+        if (j + 1 == spans.size() && left <= chunk && m >= (1 << 15)) m = ((m / 2 + 127) / 128) * 128;   // tail: halve
+        sizes.push_back(m);
+        left -= m;
       }
-      if (stage_in || stage_out) {
-        CUDA_TRY(cudaEventRecord(ctx->slot_done[slot], st));
-        pend[slot].s0 = s0;
-        pend[slot].m = m;
-        pend[slot].live = true;
-        if (stage_out && prev >= 0) {   // copy the previous chunk out while this one is on the GPU
-          rc2 = unstage(prev);
-          if (rc2) return rc2;
+      int64_t off = 0;
+      for (size_t ci = 0; ci < sizes.size(); off += sizes[ci], ++ci, slot = (slot + 1) % SpartCtx::kSlots) {
+        const int64_t m = sizes[ci], s0 = sp0 + off;
+        // one compute stream: the chunks of a span finish one after the other (on four streams they share the
+        // SMs and finish together, a span's worth of kernel time after its copy), so results flow back sooner
+        cudaStream_t st = ctx->streams[single_compute ? 0 : slot];
+        int rc2 = unstage(slot);      // pageable output: the slot's previous chunk leaves its staging buffer
+        if (rc2) return rc2;
+        trace_new(m, slot, false);
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->in_done[islot], 0));
+        if (used[slot]) CUDA_TRY(cudaStreamWaitEvent(st, ctx->slot_done[slot], 0));
+        if (ets_per_span && ci == 0 && j >= (size_t)SpartCtx::kInSlots)
+          CUDA_TRY(cudaStreamWaitEvent(st, ctx->ets_done[islot], 0));     // the span buffer's etscale array is free
+        rc2 = forward_bands_impl(ctx, sensor, (const char*)ctx->in_params[islot] + (size_t)off * elt,
+                                 ctx->in_params[islot], m, dld, broadcast_rows, precision, flags, ctx->slot_rec[slot],
+                                 ctx->slot_out[slot], st);
+        if (rc2) return rc2;
+        const size_t main_bytes = (size_t)m * nb * nout * elt;
+        if (ets_per_span)
+          CUDA_TRY(cudaMemcpyAsync((char*)ctx->in_ets[islot] + (size_t)off * elt, (char*)ctx->slot_out[slot] + main_bytes,
+                                   (size_t)m * elt, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaEventRecord(ctx->slot_k[slot], st));
+        mark(0, st);
+        CUDA_TRY(cudaStreamWaitEvent(sjoin, ctx->slot_k[slot], 0));
+        CUDA_TRY(cudaStreamWaitEvent(sout, ctx->slot_k[slot], 0));
+        if (stage_out) {
+          CUDA_TRY(cudaMemcpyAsync(ctx->stage_out[slot], ctx->slot_out[slot], main_bytes + (compact ? m * elt : 0),
+                                   cudaMemcpyDeviceToHost, sout));
+        } else {
+          CUDA_TRY(cudaMemcpyAsync(pout + (size_t)s0 * nb * nout * elt, ctx->slot_out[slot], main_bytes,
+                                   cudaMemcpyDeviceToHost, sout));
         }
-        prev = slot;
+        CUDA_TRY(cudaEventRecord(ctx->slot_done[slot], sout));
+        mark(1, sout);
+        used[slot] = true;
+        if (stage_out) {
+          pend[slot].s0 = s0;
+          pend[slot].m = m;
+          pend[slot].live = true;
+          if (prev >= 0) {            // copy the previous chunk out of its staging buffer while this one is on the GPU
+            rc2 = unstage(prev);
+            if (rc2) return rc2;
+          }
+          prev = slot;
+        }
+      }
+      CUDA_TRY(cudaEventRecord(ctx->in_free[islot], sjoin));    // every chunk of this span has been evaluated
+      if (ets_per_span) {          // (the d2h stream has already waited for the kernels of all chunks of the span)
+        CUDA_TRY(cudaMemcpyAsync(pets + (size_t)sp0 * elt, ctx->in_ets[islot], (size_t)sm * elt, cudaMemcpyDeviceToHost,
+                                 sout));
+        CUDA_TRY(cudaEventRecord(ctx->ets_done[islot], sout));
       }
     }
     for (int i = 0; i < SpartCtx::kSlots; ++i) {
@@ -2783,18 +2938,35 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
     return SPART_OK;
   };
   rc = run();
-  // on success and on failure alike: nothing of this call may still be in flight (the slot streams
-  // write into the caller's memory) when it returns
+  // on success and on failure alike: nothing of this call may still be in flight (the copy streams read and
+  // write the caller's memory) when it returns
   char keep[sizeof(g_err)];
   memcpy(keep, g_err, sizeof(keep));
-  for (int i = 0; i < SpartCtx::kSlots; ++i) {
-    const cudaError_t e = cudaStreamSynchronize(ctx->streams[i]);
+  for (int i = 0; i < SpartCtx::kSlots + 3; ++i) {
+    cudaStream_t sy = i < SpartCtx::kSlots ? ctx->streams[i]
+                                           : (i == SpartCtx::kSlots ? ctx->h2d_stream
+                                                                    : (i == SpartCtx::kSlots + 1 ? ctx->d2h_stream : ctx->join_stream));
+    const cudaError_t e = cudaStreamSynchronize(sy);
     if (e != cudaSuccess && rc == SPART_OK) {
       snprintf(keep, sizeof(keep), "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
       rc = (int)e;
     }
   }
   if (rc) memcpy(g_err, keep, sizeof(keep));
+  if (trace) {
+    fprintf(stderr, "spart_forward_bands_host trace [ms from the first enqueue]\n"
+                    "  span  <samples> <buffer> | H2D start .. end\n  chunk <samples> <slot>   | kernels end | D2H end\n");
+    for (size_t i = 0; i < tev.size(); ++i) {
+      float t[2] = {0, 0};
+      for (int k = 0; k < 2; ++k) cudaEventElapsedTime(&t[k], trace_t0, tev[i].e[k]);
+      if (tev[i].span)
+        fprintf(stderr, "  span  %7lld %d | %7.3f .. %7.3f\n", (long long)tev[i].m, tev[i].slot, t[0], t[1]);
+      else
+        fprintf(stderr, "  chunk %7lld %d |            %7.3f | %7.3f\n", (long long)tev[i].m, tev[i].slot, t[0], t[1]);
+      for (auto& e : tev[i].e) cudaEventDestroy(e);
+    }
+    cudaEventDestroy(trace_t0);
+  }
   return rc;
 }
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Host-path tuning: end-to-end rate of run_batch_params on 1M config-2 samples for several chunk sizes
-(SPART_HOST_CHUNK) and copy-thread counts (SPART_HOST_THREADS), pinned and pageable buffers.
+"""Host-path tuning: end-to-end rate of run_batch_params on 1M config-2 samples for several span / chunk sizes
+(SPART_HOST_SPAN, SPART_HOST_CHUNK; the first pair is the default), pinned and pageable buffers.
 usage (GPU box): python tools/e2e_sweep.py"""
 import json
 import os
@@ -32,7 +32,8 @@ for variant in ("compact", "compact_nobcast", "f32", "full", "pageable"):
         hin, hout = hin.pin_memory(), hout.pin_memory()
     hin.copy_(P.to(dt))
     src, dst = (hin.numpy(), hout.numpy()) if variant == "pageable" else (hin, hout)
-    for chunk in (65536, 131072, 262144):
+    for span, chunk in ((131072, 65536), (131072, 131072), (262144, 65536), (262144, 262144)):
+        os.environ["SPART_HOST_SPAN"] = str(span)
         os.environ["SPART_HOST_CHUNK"] = str(chunk)
         call = lambda: sb.run_batch_params(src, "Sentinel2A-MSI", out=dst, precision="fp32" if f32 else "fp64",
                                            broadcast_rows=bc, compact=compact)
@@ -42,6 +43,6 @@ for variant in ("compact", "compact_nobcast", "f32", "full", "pageable"):
         for _ in range(5):
             call()
         dt_s = (time.perf_counter() - t0) / 5
-        res[f"{variant}_chunk{chunk}"] = {"ms": dt_s * 1e3, "Msim_per_s": n / dt_s / 1e6}
-        print(variant, chunk, res[f"{variant}_chunk{chunk}"], flush=True)
+        res[f"{variant}_span{span}_chunk{chunk}"] = {"ms": dt_s * 1e3, "Msim_per_s": n / dt_s / 1e6}
+        print(variant, span, chunk, res[f"{variant}_span{span}_chunk{chunk}"], flush=True)
 print(json.dumps(res))
