@@ -2808,7 +2808,8 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
   auto run = [&]() -> int {
     cudaStream_t sin = ctx->h2d_stream, sout = ctx->d2h_stream, sjoin = ctx->join_stream;
     bool in_used[SpartCtx::kInSlots] = {}, used[SpartCtx::kSlots] = {};
-    int slot = 0, prev = -1;
+    int slot = 0;
+    std::vector<int> fifo;       // pageable output: slots whose chunks are still to be copied out, oldest first
     // The rows of a span buffer are ctx->in_cap elements apart whatever the span's length, so the broadcast
     // elements have fixed places: they go in once per call and buffer, while the link is still idle (a tiny copy
     // issued later, next to a saturated device->host stream, costs as much as 2 MB of payload).
@@ -2917,11 +2918,14 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
           pend[slot].s0 = s0;
           pend[slot].m = m;
           pend[slot].live = true;
-          if (prev >= 0) {            // copy the previous chunk out of its staging buffer while this one is on the GPU
-            rc2 = unstage(prev);
+          // copy finished chunks out of their staging buffers while the newer ones are on the GPU: two chunks stay
+          // in flight behind the one just enqueued (waiting for the newest would drain the pipeline)
+          fifo.push_back(slot);
+          while (fifo.size() > 2) {
+            rc2 = unstage(fifo.front());
+            fifo.erase(fifo.begin());
             if (rc2) return rc2;
           }
-          prev = slot;
         }
       }
       CUDA_TRY(cudaEventRecord(ctx->in_free[islot], sjoin));    // every chunk of this span has been evaluated
