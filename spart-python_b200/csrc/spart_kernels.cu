@@ -666,6 +666,10 @@ constexpr int kL2Threads = 128;
 constexpr int kL2Samples = 128;               // samples per block; task t = angle * kL2Samples + sample
 constexpr int kL2Tasks = 12 * kL2Samples;
 constexpr int kL2Keys = 64;                   // key classes of the counting sorts
+// Runaway guard of the step loops (votes per group).  Inside the model's domain |a| + |b| <= 1 a task needs at most
+// ~110 exact and ~460 polynomial steps (on the boundary, where the contraction rate approaches 1); outside it the
+// iteration need not converge at all (the reference would loop forever) -- such input ends here with garbage.
+constexpr int kL2MaxVotes = 1 << 15;
 
 struct Lidf2Smem {
   double x[kL2Tasks];            // x_1 -> hand-over iterate x_s (or 2 y + theta2 of a task that converged in stage A) -> F
@@ -894,7 +898,7 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
             running = !(conv || lidf2_hand(adx, yp));
           }
         }
-      } while (__any_sync(full, running) && ++iters < (1 << 22));   // the cap guards non-convergent garbage input
+      } while (__any_sync(full, running) && ++iters < kL2MaxVotes);   // the cap guards non-convergent garbage input
       if (has) {
         S.x[t] = conv ? 2.0 * y + theta2 : x;
         signed char dq;
@@ -976,7 +980,7 @@ lidf_kernel(const double* __restrict__ ab0, const double* __restrict__ ab1, int6
             running = running || (r && has[j]);
           }
         }
-      } while (__any_sync(full, running) && ++iters < (1 << 22));
+      } while (__any_sync(full, running) && ++iters < kL2MaxVotes);
 #pragma unroll
       for (int j = 0; j < NG; ++j)
         if (has[j]) {
