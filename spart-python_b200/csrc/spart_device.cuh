@@ -617,6 +617,9 @@ __device__ __forceinline__ double sail_J1(double m, double k, double LAI, double
   return (em - ek) * rcp_fast(k - m);
 }
 
+__device__ __forceinline__ double sail_J1_nb(double m, double k, double LAI, double em, double ek);
+
+template <bool kBranchFree = false>
 __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, double tau, double rs, double& rso,
                                             double& rdo, double& rsd, double& rdd) {
   const double k = G.k, K = G.K, bf = G.bf, LAI = G.LAI;
@@ -640,9 +643,9 @@ __device__ __forceinline__ void sailh_point(const CanopyGeo& G, double rho, doub
   const double e2 = e1 * e1;
   const double tau_ss = G.tau_ss, tau_oo = G.tau_oo;
   const double inv_km = rcp_fast(k + m), inv_Km = rcp_fast(K + m);
-  const double J1k = sail_J1(m, k, LAI, e1, tau_ss);
+  const double J1k = kBranchFree ? sail_J1_nb(m, k, LAI, e1, tau_ss) : sail_J1(m, k, LAI, e1, tau_ss);
   const double J2k = (1.0 - tau_ss * e1) * inv_km;   // calcJ2 at x = 0 (sailh.py:172-177)
-  const double J1K = sail_J1(m, K, LAI, e1, tau_oo);
+  const double J1K = kBranchFree ? sail_J1_nb(m, K, LAI, e1, tau_oo) : sail_J1(m, K, LAI, e1, tau_oo);
   const double J2K = (1.0 - tau_oo * e1) * inv_Km;
   const double re = rinf * e1;
   const double inv_den = rcp_fast(1.0 - rinf2 * rinf2);
@@ -797,6 +800,105 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
     acc = fma(c_gl6_w[i], exp_fast(arg), acc);
   }
   pso2w = 0.5 * acc;
+}
+
+// ---- branch-free variants for the paired-knot path of band_kernel -----------------------------------------
+// A Sentinel-2 band centre lies between two grid wavelengths, so band_kernel evaluates leaf, soil and canopy at
+// two knots per band.  The two evaluations are independent; written as straight-line code without branches they
+// sit in one basic block and the compiler interleaves them, which gives every warp two independent FP64 chains
+// (FP64 instructions issued back to back by one warp keep the pipe's 2-cycle cadence, those of different warps
+// follow each other every 3 cycles, tools/micro/fp64_latency.cu).  MEASURED: no gain (SPART_BAND_PAIR, off by
+// default) -- with register operands the pipe runs at ~2.9 cycles per instruction either way.  Each function performs the operations of its
+// branching original on the lanes the original would have executed them on (the other form's result is
+// computed and dropped by a select), so the results are bit-identical.
+__device__ __forceinline__ double plate_tau_nb(double K, const TauTable* tab) {
+  // caller guarantees K > 0
+  const double emk = exp_neg(-K);
+  const double t = rcp_fast(K);
+  const bool small = K < 1.0;
+  const int e = (__double2hiint(K) >> 20) - 1023;   // floor(log2 K) for K >= 1
+  const int idx = small ? 0 : min(e + 1, SPART_TAU_NINT - 1);
+  const double u = small ? 2.0 * K - 1.0 : (t - tab->mid[idx]) * tab->invhalf[idx];
+  const double p = poly_eval<SPART_TAU_DEG, SPART_TAU_SPLIT>(tab->coef[idx], u);
+  const double lg = log_fast(small ? K : 1.0);
+  const double e1 = fma(K, p, -0.57721566490153286061 - lg);
+  const double r_small = (1.0 - K) * emk + K * K * e1;
+  const double r_big = emk * t * p;
+  return small ? r_small : r_big;
+}
+
+__device__ __forceinline__ void leaf_from_tau_nb(double tau, double t_alph, double t12, double t21, double N,
+                                                 double& refl, double& tran) {
+  const double r_alph = 1.0 - t_alph, r12 = 1.0 - t12, r21 = 1.0 - t21;
+  const double tt21 = tau * t21;
+  const double inv_d1 = rcp_fast(1.0 - r21 * r21 * tau * tau);
+  const double Ta = t_alph * tt21 * inv_d1;
+  const double Ra = r_alph + r21 * tau * Ta;
+  const double t = t12 * tt21 * inv_d1;
+  const double r = r12 + r21 * tau * t;
+  const double Nm1 = N - 1.0;
+  const bool zero_abs = r + t >= 1.0;                  // prospect_5d.py:233-235
+  const double Tz = t * rcp_fast(t + (1.0 - t) * Nm1);
+  const double D = sqrt_fast((1.0 + r + t) * (1.0 + r - t) * (1.0 - r + t) * (1.0 - r - t));
+  const double rq = r * r, tq = t * t;
+  const double a = (1.0 + rq - tq + D) * rcp_fast(2.0 * r);
+  const double b = (1.0 - rq + tq + D) * rcp_fast(2.0 * t);
+  const double bNm1 = (Nm1 == 0.0) ? 1.0 : exp_clamp(Nm1 * log_fast(b));
+  const double bN2 = bNm1 * bNm1;
+  const double a2 = a * a;
+  const double inv_d2 = rcp_fast(a2 * bN2 - 1.0);
+  const double Rsub = zero_abs ? 1.0 - Tz : a * (bN2 - 1.0) * inv_d2;
+  const double Tsub = zero_abs ? Tz : bNm1 * (a2 - 1.0) * inv_d2;
+  const double inv_d3 = rcp_fast(1.0 - Rsub * r);
+  tran = Ta * Tsub * inv_d3;
+  refl = Ra + Ta * Rsub * t * inv_d3;
+}
+
+__device__ __forceinline__ void prospect_point_nb(const LeafPar& L, const double* lc, const TauTable* tab,
+                                                  double& refl, double& tran) {
+  const double Ksum = L.Cab * lc[LC_KAB] + L.Cca * lc[LC_KCA] + L.Cdm * lc[LC_KDM] + L.Cw * lc[LC_KW] +
+                      L.Cs * lc[LC_KS] + L.Cant * lc[LC_KANT] + L.CBC * lc[LC_CBC] + L.PROT * lc[LC_PROT];
+  const double Kall = Ksum * L.invN;
+  const bool pos = Kall > 0.0;
+  const double tk = plate_tau_nb(pos ? Kall : 1.0, tab);
+  leaf_from_tau_nb(pos ? tk : 1.0, lc[LC_TALPH], lc[LC_T12], lc[LC_T21], L.N, refl, tran);
+}
+
+// BSM at two wavelengths (same sample): bsm_point twice, side by side
+__device__ __forceinline__ void bsm_pair(const SoilPar& S, const double* lc0, const double* lc1, double& rwet0,
+                                         double& rwet1) {
+  const double rdry0 = S.f1 * lc0[LC_GSV0] + S.f2 * lc0[LC_GSV1] + S.f3 * lc0[LC_GSV2];
+  const double rdry1 = S.f1 * lc1[LC_GSV0] + S.f2 * lc1[LC_GSV1] + S.f3 * lc1[LC_GSV2];
+  rwet0 = rdry0;
+  rwet1 = rdry1;
+  if (S.mu > 0.0) {
+    const double rbac0 = 1.0 - (1.0 - rdry0) * (rdry0 * lc0[LC_SOILC1] + 1.0 - rdry0);
+    const double rbac1 = 1.0 - (1.0 - rdry1) * (rdry1 * lc1[LC_SOILC1] + 1.0 - rdry1);
+    const double p0 = lc0[LC_SOILP], Rw0 = lc0[LC_SOILRW], p1 = lc1[LC_SOILP], Rw1 = lc1[LC_SOILRW];
+    const double tw10 = exp_neg(-2.0 * lc0[LC_KW] * S.film), tw11 = exp_neg(-2.0 * lc1[LC_KW] * S.film);
+    double fk = S.emu;
+    double acc0 = rdry0 * fk, acc1 = rdry1 * fk;
+    double tw0 = 1.0, tw1 = 1.0;
+    const double g0 = (1.0 - Rw0) * (1.0 - p0), g1 = (1.0 - Rw1) * (1.0 - p1);
+#pragma unroll
+    for (int k = 1; k <= 6; ++k) {
+      tw0 *= tw10;
+      tw1 *= tw11;
+      fk = fk * S.mu * (1.0 / (double)k);
+      const double x0 = tw0 * rbac0, x1 = tw1 * rbac1;
+      acc0 += (Rw0 + g0 * x0 * rcp_fast(1.0 - p0 * x0)) * fk;
+      acc1 += (Rw1 + g1 * x1 * rcp_fast(1.0 - p1 * x1)) * fk;
+    }
+    rwet0 = acc0;
+    rwet1 = acc1;
+  }
+}
+
+__device__ __forceinline__ double sail_J1_nb(double m, double k, double LAI, double em, double ek) {
+  const bool close = fabs((m - k) * LAI) < 1e-6;
+  const double s = 0.5 * (em + ek) * LAI * (1.0 - (1.0 / 12.0) * (k - m) * (k - m) * LAI * LAI);
+  const double d = (em - ek) * rcp_fast(k - m);
+  return close ? s : d;
 }
 
 // ---- SMAC atmosphere at one band (smac.py:94-207) + TOC->TOA (SPART.py:235-252) ---------

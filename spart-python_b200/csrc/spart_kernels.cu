@@ -44,8 +44,15 @@ using namespace spart;
 #ifndef SPART_BAND_SMEM_STATE
 #define SPART_BAND_SMEM_STATE 1
 #endif
+// SPART_BAND_PAIR = 1: the two interpolation knots of a band are evaluated side by side (see plate_tau_nb).
+// Bit-identical, measured SLOWER: 0.620 ms (128 registers, 4 blocks/SM), 0.622 (96 registers, spills), 0.683 (168
+// registers, 3 blocks) against 0.602 ms -- the FP64 pipe gains nothing from a second chain per warp when the
+// operands come from registers (tools/micro/fp64_horner.cu).  Kept as a build knob.
+#ifndef SPART_BAND_PAIR
+#define SPART_BAND_PAIR 0
+#endif
 #ifndef SPART_BAND_MINBLOCKS_U
-#define SPART_BAND_MINBLOCKS_U 5
+#define SPART_BAND_MINBLOCKS_U (SPART_BAND_PAIR ? 4 : 5)
 #endif
 #ifndef SPART_SRF_MINBLOCKS
 #define SPART_SRF_MINBLOCKS 5
@@ -1360,6 +1367,29 @@ band_kernel(const Params P, int64_t n, const double* __restrict__ rec,
     // PROSPECT + BSM + SAILH at the one or two wavelengths np.interp touches (SPART.py:220-223)
     double rso = 0.0, rdo = 0.0, rsd = 0.0, rdd = 0.0;
     const int npts = (__double2hiint(bt[BT_NPTS]) >= 0x40000000) ? 2 : 1;   // 2.0 or 1.0, integer-pipe test
+#if SPART_BAND_PAIR && SPART_BAND_SMEM_STATE
+    if (npts == 2) {
+      const double* lc0 = &bt[BT_LC0];
+      const double* lc1 = &bt[BT_LC1];
+      double refl0, tran0, refl1, tran1, rwet0, rwet1;
+      prospect_point_nb(L, lc0, &s_tau, refl0, tran0);
+      prospect_point_nb(L, lc1, &s_tau, refl1, tran1);
+      volatile double(*st)[kBandThreads] = s_st;
+      const int t = threadIdx.x;
+      S.f1 = st[0][t]; S.f2 = st[1][t]; S.f3 = st[2][t]; S.mu = st[3][t]; S.emu = st[4][t]; S.film = st[5][t];
+      bsm_pair(S, lc0, lc1, rwet0, rwet1);
+      G.LAI = st[6][t]; G.k = st[7][t]; G.K = st[8][t]; G.bf = st[9][t]; G.sob = st[10][t]; G.sof = st[11][t];
+      G.tau_ss = st[12][t]; G.tau_oo = st[13][t]; G.sumpso = st[14][t]; G.pso2w = st[15][t]; G.Z = st[16][t];
+      double b0, b1, b2, b3;
+      sailh_point<true>(G, refl0, tran0, rwet0, rso, rdo, rsd, rdd);
+      sailh_point<true>(G, refl1, tran1, rwet1, b0, b1, b2, b3);
+      const double fr = bt[BT_FRAC];
+      rso = (b0 - rso) * fr + rso;
+      rdo = (b1 - rdo) * fr + rdo;
+      rsd = (b2 - rsd) * fr + rsd;
+      rdd = (b3 - rdd) * fr + rdd;
+    } else
+#endif
 #pragma unroll 1
     for (int pt = 0; pt < npts; ++pt) {
       const double* lc = &bt[BT_LC0 + pt * LC_COUNT];
