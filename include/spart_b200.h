@@ -171,7 +171,7 @@ int spart_forward_bands(const SpartCtx* ctx, int32_t sensor, const void* params_
  * copy engines and the SMs run side by side.  Pinned or registered buffers (cudaHostAlloc /
  * cudaHostRegister / torch pin_memory) are
  * DMA'd directly; pageable buffers (plain NumPy arrays) are staged through internal pinned
- * buffers by a small pool of copy threads (SPART_HOST_THREADS, default 8), because an asynchronous
+ * buffers by a small pool of copy threads (SPART_HOST_THREADS, default 12), because an asynchronous
  * copy on pageable memory degenerates to a synchronous single-threaded driver copy.  Broadcast
  * rows move one element.  Returns when out_host is complete; on failure no copy is left in
  * flight.  This is the drop-in for a caller that holds NumPy arrays. */

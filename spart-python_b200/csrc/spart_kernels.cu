@@ -2710,7 +2710,7 @@ static int ensure_slots(SpartCtx* ctx, int64_t span, int64_t chunk, size_t out_b
   if (stage_in && ctx->stage_in_cap < in_bytes) ctx->stage_in_cap = in_bytes;
   if (stage_out && ctx->stage_out_cap < out_bytes) ctx->stage_out_cap = out_bytes;
   if ((stage_in || stage_out) && !ctx->pool) {
-    int want = 8;
+    int want = 12;      // copy threads: 4 / 8 / 12 / 16 -> 60 / 85 / 98 / 94 M simulations/s from pageable arrays
     if (const char* e = getenv("SPART_HOST_THREADS")) want = atoi(e);
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0 && want > hw) want = hw;
