@@ -717,8 +717,8 @@ __device__ __forceinline__ float lidf2_lg2(float x) {
 //   |2 dx / (1 - y')| <= R (1 - lam)^(1/3) with R = 0.15 (the cube root keeps slowly converging tasks, whose Newton
 //   estimate is poor and whose errors contract slowly, on exact steps for longer): 2.0 exact steps per task
 //   instead of 4.3 on the benchmark distribution (the first one is free) for 2.2 more polynomial steps, F within
-//   9e-16 of the step-by-step iteration over the whole |a| + |b| <= 1 domain, its boundary included (NumPy
-//   prototype with the kernel's arithmetic, 1.3e5 samples; GPU: tools/lidf_parity_scale.py).  The test is
+//   9e-16 of the step-by-step iteration over the whole |a| + |b| <= 1 domain, its boundary included
+//   (tools/check_lidf_centred.py: NumPy prototype with the kernel's arithmetic; GPU: tools/lidf_parity_scale.py).  The test is
 //   written without a division: 8 |dx|^3 <= R^3 (1 - y')^3 (1 - y') / 2.
 __device__ __forceinline__ bool lidf2_hand(double adx, double yp) {
 #if SPART_LIDF2_CENTRED
