@@ -53,3 +53,22 @@ def test_gpu_on_threshold_straddling_cases():
     out = sb.run_batch_params(torch.from_numpy(np.ascontiguousarray(P.T)).cuda(), "LANDSAT8-OLI").cpu().numpy()
     assert relerr(out, so.spart_bands(P, "LANDSAT8-OLI")) < 1.5e-9
     print("threshold cases:", len(ab), "GPU and oracle stop on different steps in", flips)
+
+
+def test_centred_taylor_model_reproduces_the_iteration():
+    """CPU prototype of lidf_kernel's scheme (tools/check_lidf_centred.py: exact steps, then a degree-6 Taylor
+    model centred on the Newton estimate of the fixed point, hand-over radius 0.15): over the |a| + |b| <= 1
+    domain and its boundary the resulting lidf is within a few ulp of the reference's step-by-step iteration,
+    i.e. the same iterates and the same step counts."""
+    import check_lidf_centred as proto
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-1, 1, 4000)
+    b = rng.uniform(-1, 1, 4000)
+    keep = np.abs(a) + np.abs(b) <= 1
+    ae = rng.uniform(-1, 1, 500)
+    a = np.concatenate([a[keep], ae, [1.0, -1.0, 0.0, 0.0, -0.35]])
+    b = np.concatenate([b[keep], (1 - np.abs(ae)) * rng.choice([-1, 1], 500), [0.0, 0.0, 1.0, -1.0, -0.15]])
+    lidf, it_exact, it_poly = proto.lidf_centred(a, b, 0.15)
+    assert np.abs(lidf - so.leafangles(a, b)).max() < 5e-15
+    inner = (np.abs(a) <= 0.5) & (np.abs(b) <= 0.5)
+    assert it_exact[inner].mean() / 12 < 2.2          # 4.3 with the hand-over at 1.6e-2 around the iterate
