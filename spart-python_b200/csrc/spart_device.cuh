@@ -700,11 +700,22 @@ __device__ __forceinline__ void volscatt_class(double sin_tts, double cos_tts, d
   // the quotient is exactly -1 whenever Cs >= Ss (As == Cs) -- acos amplifies a 1-ulp deviation from -1 to
   // 1e-8, so that case is a select; otherwise -Cs / Ss comes from the fast reciprocal (<= 1 ulp; chi_s, chi_o are
   // stationary in bts, bto there, and the reference's own correctly rounded quotient is as ill-conditioned)
-  const double zs = (Cs >= Ss) ? -1.0 : -Cs * rcp_fast(Ss);
-  const double zo = (Co >= So) ? -1.0 : -Co * rcp_fast(So);
-  const double bts = acos(zs), bto = acos(zo);
-  // sin(acos z) = sqrt(1 - z^2) (>= 0 on [0, pi]); differs from sin of the rounded angle by < 2e-16 absolute
-  const double sbts = sqrt_fast(fma(-zs, zs, 1.0)), sbto = sqrt_fast(fma(-zo, zo, 1.0));
+  // For the flat leaf classes (leaf angle + zenith angle <= 90 degrees) C >= S holds in every lane of the warp:
+  // beta = acos(-1) = pi and sin beta = 0 exactly, no reciprocal, acos and square root (warp-uniform branch; the
+  // calling lanes of a warp are converged here)
+  double zs = -1.0, zo = -1.0, bts = SPART_PI, bto = SPART_PI, sbts = 0.0, sbto = 0.0;
+  const unsigned active = __activemask();
+  if (!__all_sync(active, Cs >= Ss)) {
+    zs = (Cs >= Ss) ? -1.0 : -Cs * rcp_fast(Ss);
+    bts = acos(zs);
+    // sin(acos z) = sqrt(1 - z^2) (>= 0 on [0, pi]); differs from sin of the rounded angle by < 2e-16 absolute
+    sbts = sqrt_fast(fma(-zs, zs, 1.0));
+  }
+  if (!__all_sync(active, Co >= So)) {
+    zo = (Co >= So) ? -1.0 : -Co * rcp_fast(So);
+    bto = acos(zo);
+    sbto = sqrt_fast(fma(-zo, zo, 1.0));
+  }
   chi_o = 2.0 / SPART_PI * ((bto - SPART_PI / 2.0) * Co + sbto * So);
   chi_s = 2.0 / SPART_PI * ((bts - SPART_PI / 2.0) * Cs + sbts * Ss);
   const double delta1 = fabs(bts - bto);

@@ -298,10 +298,19 @@ __device__ __forceinline__ void volscatt_class_f(float sin_tts, float cos_tts, f
   const float Cs = cos_ttli * cos_tts, Ss = sin_ttli * sin_tts;
   const float Co = cos_ttli * cos_tto, So = sin_ttli * sin_tto;
   const float As = fmaxf(Ss, Cs), Ao = fmaxf(So, Co);
-  const float cbs = -Cs / As, cbo = -Co / Ao;     // exact: the quotient must be exactly -1 when As == Cs
-  const float bts = acosf(cbs), bto = acosf(cbo);
-  // sin(acos z) = sqrt(1 - z^2)
-  const float sbo = fsqrt(fmaxf(0.0f, 1.0f - cbo * cbo)), sbs = fsqrt(fmaxf(0.0f, 1.0f - cbs * cbs));
+  // flat leaf classes: C >= S in every lane of the warp -> beta = pi, sin beta = 0 (see volscatt_class)
+  float cbs = -1.0f, cbo = -1.0f, bts = SPART_PI_F, bto = SPART_PI_F, sbs = 0.0f, sbo = 0.0f;
+  const unsigned active = __activemask();
+  if (!__all_sync(active, Cs >= Ss)) {
+    cbs = -Cs / As;                               // exact: the quotient must be exactly -1 when As == Cs
+    bts = acosf(cbs);
+    sbs = fsqrt(fmaxf(0.0f, 1.0f - cbs * cbs));   // sin(acos z) = sqrt(1 - z^2)
+  }
+  if (!__all_sync(active, Co >= So)) {
+    cbo = -Co / Ao;
+    bto = acosf(cbo);
+    sbo = fsqrt(fmaxf(0.0f, 1.0f - cbo * cbo));
+  }
   chi_o = 2.0f / SPART_PI_F * ((bto - SPART_PI_F / 2.0f) * Co + sbo * So);
   chi_s = 2.0f / SPART_PI_F * ((bts - SPART_PI_F / 2.0f) * Cs + sbs * Ss);
   const float delta1 = fabsf(bts - bto);
