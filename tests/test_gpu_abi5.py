@@ -180,6 +180,42 @@ def test_host_path_pageable_and_pinned(env):
     assert np.array_equal(c.full(), dev)
 
 
+def test_host_path_many_spans_and_chunks(env, monkeypatch):
+    """Small spans / chunks (SPART_HOST_SPAN / SPART_HOST_CHUNK) so that the three span buffers and the four
+    output slots are reused several times within one call: pinned and pageable buffers, full / compact / float32
+    results, a ragged tail, broadcast rows (their elements are written once per call and buffer)."""
+    torch, sb, so = env
+    monkeypatch.setenv("SPART_HOST_SPAN", "4096")
+    monkeypatch.setenv("SPART_HOST_CHUNK", "1024")
+    n = 11 * 4096 + 1234 + 77
+    P = so.synthetic_params(n, 2, seed=21)
+    P[:, so.LIDFA], P[:, so.LIDFB] = -0.35, -0.15
+    rows = [7, 8, 13, 14, so.LIDFA, so.LIDFB, 19, 20, 21]
+    pt = np.ascontiguousarray(P.T)
+    Q = pt.copy()
+    Q[rows, 1:] = np.nan                                   # only element 0 of a broadcast row may be read
+    dev = sb.run_batch_params(torch.from_numpy(pt).cuda(), "Sentinel2A-MSI", broadcast_rows=rows).cpu().numpy()
+    assert np.array_equal(sb.run_batch_params(Q, "Sentinel2A-MSI", broadcast_rows=rows), dev)
+    pin_in = torch.from_numpy(Q).pin_memory()
+    pin_out = torch.empty((n, 13, 3), dtype=torch.float64).pin_memory()
+    sb.run_batch_params(pin_in, "Sentinel2A-MSI", out=pin_out, broadcast_rows=rows)
+    assert np.array_equal(pin_out.numpy(), dev)
+    c = sb.run_batch_params(pin_in, "Sentinel2A-MSI", broadcast_rows=rows, compact=True)     # etscale once per span
+    assert np.array_equal(np.asarray(c.full()), dev)
+    c2 = sb.run_batch_params(Q, "Sentinel2A-MSI", broadcast_rows=rows, compact=True)
+    assert np.array_equal(np.asarray(c2.full()), dev)
+    dev32 = sb.run_batch_params(torch.from_numpy(pt.astype(np.float32)).cuda(), "Sentinel2A-MSI", precision="fp32",
+                                broadcast_rows=rows).cpu().numpy()
+    h32 = sb.run_batch_params(torch.from_numpy(Q.astype(np.float32)).pin_memory(), "Sentinel2A-MSI",
+                              precision="fp32", broadcast_rows=rows, compact=True)
+    assert np.array_equal(np.asarray(h32.full()), dev32)
+    # no broadcast rows at all, general geometry, a second sensor
+    P3 = so.synthetic_params(9000, 3, seed=22)
+    p3 = np.ascontiguousarray(P3.T)
+    d3 = sb.run_batch_params(torch.from_numpy(p3).cuda(), "LANDSAT8-OLI").cpu().numpy()
+    assert np.array_equal(sb.run_batch_params(p3, "LANDSAT8-OLI"), d3)
+
+
 def test_thermal_leaf_optics_are_passed_through(env):
     """LeafBiology.rho_thermal / tau_thermal (SPART.py:461-466) reach leafopt and canopyopt."""
     torch, sb, so = env
