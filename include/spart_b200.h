@@ -37,8 +37,10 @@
  * for the whole batch BY CONSTRUCTION -- the library evaluates the sample-independent volume
  * scattering terms (_volscatt, sailh.py:401-446) and the geometry-only sub-expressions of SMAC
  * (smac.py:125-201) once per thread block instead of once per sample.  Results agree with the
- * general path to a few ulp (sums are re-associated).  There is no unchecked "the caller promises"
- * flag: a row is either read per sample or read once.
+ * general path to a few ulp (sums are re-associated).  When bits 16 and 17 (LIDFa, LIDFb) are both
+ * set the leaf inclination distribution (calculate_leafangles, sailh.py:351-398) is iterated once for
+ * the whole batch (bit-identical results).  There is no unchecked "the caller promises" flag: a row
+ * is either read per sample or read once.
  */
 #ifndef SPART_B200_H
 #define SPART_B200_H
