@@ -627,8 +627,9 @@ lidf_kernel_v1(const double* __restrict__ ab0, const double* __restrict__ ab1, i
 // lidf_kernel_v1 above treats a warp's (sample, angle) tasks as a queue; with task lengths of 1..26 exact and
 // 3..84 polynomial steps (mean 4.3 / 19.9 on the benchmark distribution) its lanes spend ~45 % of the issued
 // instructions in rounds they have already finished or in divergent hand-out code (tools/lidf_queue_sim.py).
-// Version 2 runs exactly the same arithmetic per task -- results are bit-identical -- but orders the work by
-// *predicted* length first:
+// Version 2 runs the same iterations per task (with SPART_LIDF2_CENTRED = 0 the very same arithmetic: results
+// are bit-identical; with the centred Taylor model of the default build F agrees to 1e-15, see lidf2_hand) but
+// orders the work by *predicted* length first:
 //   A1  the first exact step of all 12 x 128 tasks of a block, without a sincos (x0 = theta2 is one of twelve
 //       constants, whose sine / cosine sit in a table filled by the same sincos_small); from its |dx| and
 //       y'(x0) the linear-convergence model predicts the remaining exact steps (or, for a task that hands
