@@ -401,6 +401,13 @@ def rooflines(cx, tag, kern_ms, n_launch, step_ms, nb_total, cfg_bytes):
         "kernel_ms": kern_ms, "kernel_frac": per, "share_of_step": kern_ms[dominant] / step_ms,
         "step_frac": (tot_flop * n_launch / (tot_ms * 1e-3) / 1e12 / peaks["fp64_tflops"]) if tot_flop else None,
         "step_frac_clock_peak": (tot_flop * n_launch / (tot_ms * 1e-3) / 1e12 / clock_peak) if tot_flop else None,
+        # the FP64 issue ceiling of dependent chains on register operands (FP64 instructions of different warps
+        # issue every 3 cycles on the B200): measured live, ~2/3 of the DFMA-chain peak
+        "register_chain_peak": peaks.get("fp64_register_chain_tflops"),
+        "frac_register_chain_peak": (ach / peaks["fp64_register_chain_tflops"])
+        if (ach and peaks.get("fp64_register_chain_tflops")) else None,
+        "step_frac_register_chain_peak": (tot_flop * n_launch / (tot_ms * 1e-3) / 1e12 / peaks["fp64_register_chain_tflops"])
+        if (tot_flop and peaks.get("fp64_register_chain_tflops")) else None,
         "flop_per_simulation": {k: flop.get(k) for k in KERNELS}, "flop_count_note": cx.flop_note,
         "kernel_build": kernel_source_sha(),
     }

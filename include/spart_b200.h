@@ -254,6 +254,12 @@ int spart_profile_read(SpartCtx* ctx, double* kernel_ms, int64_t* calls);
  * chains on all SMs.  Results in TFLOP/s (FMA = 2 flop). */
 int spart_measure_peaks(int32_t device, double* fp64_tflops, double* fp32_tflops);
 
+/* The FP64 rate of DEPENDENT DFMA chains on register operands, one chain per warp, eight warps per
+ * scheduler (a degree-6 Horner step): on the B200 FP64 instructions of different warps issue every
+ * 3 cycles, not 2, so this is ~2/3 of spart_measure_peaks' FP64 figure -- the issue ceiling of the
+ * leaf-angle / geometry / band kernels, reported by bench.py beside the DFMA-chain peak. */
+int spart_measure_fp64_chain(int32_t device, double* tflops);
+
 /* Number of kernel launches this library has enqueued on this thread since load. */
 int64_t spart_launch_count(void);
 

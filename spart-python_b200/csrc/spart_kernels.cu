@@ -1882,6 +1882,54 @@ __global__ void fma_chain_kernel(T* out, int iters, T a, T b) {
   if (r == (T)-12345.678) out[0] = r;   // never true; keeps the chain alive
 }
 
+// Dependent DFMA chains on register operands, one chain per warp: a degree-6 Horner step u <- g(u) with seven
+// per-thread coefficients (the inner loop of lidf_kernel's stage B without its compare).  Eight warps per
+// scheduler; what this sustains is the FP64 issue ceiling of code like the leaf-angle / band kernels.
+__global__ void __launch_bounds__(1024, 1) fp64_register_chain_kernel(double* out, int iters) {
+  double g[7];
+  const double base[7] = {0.01, 0.45, 0.1, -0.05, 0.01, 0.002, -0.0003};    // a contraction towards ~0.018
+#pragma unroll
+  for (int k = 0; k < 7; ++k) g[k] = base[k] * (1.0 + 1e-9 * threadIdx.x);
+  double u = 1e-6 * threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int rep = 0; rep < 4; ++rep) {
+      double r = g[6];
+#pragma unroll
+      for (int k = 5; k >= 0; --k) r = fma(r, u, g[k]);
+      u = r;
+    }
+  }
+  if (u == -12345.678) out[0] = u;   // never true; keeps the chain alive
+}
+
+static int time_register_chain(int sm_count, double* tflops) {
+  double* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(double)));
+  const int iters = 1 << 12, threads = 1024, blocks = sm_count;     // 8 warps per scheduler
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    fp64_register_chain_kernel<<<blocks, threads>>>(d, iters);
+    ++g_launches;
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 6.0 * 4.0 * (double)iters * threads * (double)blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return SPART_OK;
+}
+
 template <typename T>
 static int time_fma(int sm_count, double* tflops) {
   T* d = nullptr;
@@ -3020,6 +3068,17 @@ int spart_measure_peaks(int32_t device, double* fp64_tflops, double* fp32_tflops
   int rc = time_fma<double>(sm, fp64_tflops);
   if (rc) return rc;
   return time_fma<float>(sm, fp32_tflops);
+}
+
+int spart_measure_fp64_chain(int32_t device, double* tflops) {
+  if (!tflops) return fail(SPART_EINVAL, "spart_measure_fp64_chain: null argument%s");
+  const int ndev = spart_device_count();
+  if (ndev <= 0) return fail(SPART_ENODEV, "spart_measure_fp64_chain: no CUDA device%s");
+  if (device < 0 || device >= ndev) return fail(SPART_EINVAL, "spart_measure_fp64_chain: device index out of range%s");
+  GUARD_DEVICE(device);
+  int sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+  return time_register_chain(sm, tflops);
 }
 
 }  // extern "C"

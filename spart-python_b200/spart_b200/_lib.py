@@ -31,7 +31,7 @@ EXPORTS = (
     "spart_abi_version", "spart_last_error", "spart_device_count", "spart_create", "spart_destroy",
     "spart_workspace_bytes", "spart_forward_bands", "spart_forward_bands_host", "spart_forward_spectrum",
     "spart_smac", "spart_sailh", "spart_lut_workspace_bytes", "spart_lut_nearest", "spart_lut_nearest_tc", "spart_lut_unpack",
-    "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_launch_count",
+    "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_measure_fp64_chain", "spart_launch_count",
 )
 
 
@@ -96,6 +96,7 @@ def load():
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]
     lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]
     lib.spart_measure_peaks.argtypes = [c_int32, POINTER(c_double), POINTER(c_double)]
+    lib.spart_measure_fp64_chain.argtypes = [c_int32, POINTER(c_double)]
     lib.spart_launch_count.restype = c_int64
     if lib.spart_abi_version() != ABI_VERSION:
         raise SpartError(f"libspart_b200.so ABI {lib.spart_abi_version()} != expected {ABI_VERSION}")

@@ -377,7 +377,9 @@ class Engine:
         a, b = _lib.c_double(), _lib.c_double()
         _lib.check(self.lib.spart_measure_peaks(self.device.index, _lib.byref(a), _lib.byref(b)),
                    "spart_measure_peaks")
-        return {"fp64_tflops": a.value, "fp32_tflops": b.value}
+        c = _lib.c_double()
+        _lib.check(self.lib.spart_measure_fp64_chain(self.device.index, _lib.byref(c)), "spart_measure_fp64_chain")
+        return {"fp64_tflops": a.value, "fp32_tflops": b.value, "fp64_register_chain_tflops": c.value}
 
     def launch_count(self):
         return int(self.lib.spart_launch_count())
