@@ -814,8 +814,8 @@ __device__ __forceinline__ void hotspot_integrals(double K, double k, double LAI
 }
 
 // ---- branch-free variants for the paired-knot path of band_kernel -----------------------------------------
-// A Sentinel-2 band centre lies between two grid wavelengths, so band_kernel evaluates leaf, soil and canopy at
-// two knots per band.  The two evaluations are independent; written as straight-line code without branches they
+// A band whose centre lies between two grid wavelengths (all MODIS bands, half of the OLCI bands; the
+// Sentinel-2 / Landsat-8 tables have integer centres) is evaluated at two knots.  The two evaluations are independent; written as straight-line code without branches they
 // sit in one basic block and the compiler interleaves them, which gives every warp two independent FP64 chains
 // (FP64 instructions issued back to back by one warp keep the pipe's 2-cycle cadence, those of different warps
 // follow each other every 3 cycles, tools/micro/fp64_latency.cu).  MEASURED: no gain (SPART_BAND_PAIR, off by

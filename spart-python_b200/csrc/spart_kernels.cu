@@ -44,10 +44,11 @@ using namespace spart;
 #ifndef SPART_BAND_SMEM_STATE
 #define SPART_BAND_SMEM_STATE 1
 #endif
-// SPART_BAND_PAIR = 1: the two interpolation knots of a band are evaluated side by side (see plate_tau_nb).
-// Bit-identical, measured SLOWER: 0.620 ms (128 registers, 4 blocks/SM), 0.622 (96 registers, spills), 0.683 (168
-// registers, 3 blocks) against 0.602 ms -- the FP64 pipe gains nothing from a second chain per warp when the
-// operands come from registers (tools/micro/fp64_horner.cu).  Kept as a build knob.
+// SPART_BAND_PAIR = 1: the two interpolation knots of a band with a fractional centre wavelength are evaluated side
+// by side (see plate_tau_nb).  Bit-identical; measured: TerraAqua-MODIS (20 bands x 2 knots) 1.558 -> 1.529 ms at
+// 128 registers / 4 blocks per SM (1.559 at 96 registers), Sentinel-3 OLCI 1.283 -> 1.395 ms, and 3 % SLOWER on the
+// one-knot sensors of the benchmark (Sentinel-2A 0.602 -> 0.620 ms): the FP64 pipe gains nothing from a second chain
+// per warp when the operands come from registers (tools/micro/fp64_horner.cu).  Kept as a build knob, off.
 #ifndef SPART_BAND_PAIR
 #define SPART_BAND_PAIR 0
 #endif
