@@ -96,7 +96,12 @@ enum {
    * extraterrestrial scale cf(DOY) cos(sza) / pi (SPART.py:345-353).  L_TOA is then rebuilt by the
    * consumer bit for bit as (conv_ea[b] * etscale[s]) * R_TOA[s][b] -- the product the kernels
    * themselves form (SPART.py:252); conv_ea is the SpartSensor member.  Two thirds of the bytes. */
-  SPART_FLAG_COMPACT_OUT = 32
+  SPART_FLAG_COMPACT_OUT = 32,
+  /* SPART_FP64, device path: the workspace already holds a caller-supplied leaf inclination
+   * distribution (spart_set_lidf on the same workspace and stream): LIDFa / LIDFb are ignored, the
+   * leaf-angle kernel is skipped and the 13 values enter k, K, bf, sob, sof as they are -- what the
+   * reference does with an assigned CanopyStructure.lidf (sailh.py:81-97 read canopy.lidf). */
+  SPART_FLAG_USER_LIDF = 64
 };
 
 /* elements of the result buffer of spart_forward_bands for n samples, nb bands and these flags */
@@ -181,6 +186,11 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
                              int64_t n, int64_t ld, uint32_t broadcast_rows, int32_t precision,
                              int32_t flags, void* out_host);
 
+/* Stores a caller-supplied leaf inclination distribution, lidf_dev [n][13] of double (the 13 classes
+ * of sailh.py:49, each row summing to 1), in the workspace of a batch of n samples; the following
+ * spart_forward_bands call on that workspace passes SPART_FLAG_USER_LIDF.  Asynchronous on stream. */
+int spart_set_lidf(const double* lidf_dev, int64_t n, void* workspace_dev, void* stream);
+
 /* Replaces the leafopt / soilopt / canopyopt attributes of a SPART object after run()
  * (SPART.py:192-214, 427-470): full 2162-wavelength spectra.
  * out_dev: double [n][SPART_NSPEC][SPART_NWL_S], planes
@@ -188,7 +198,7 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
  *   (value at 2400 nm beyond)  5 rso  6 rdo  7 rsd  8 rdd.
  * rho_thermal / tau_thermal: leaf reflectance / transmittance beyond 2400 nm
  * (LeafBiology.rho_thermal / tau_thermal, prospect_5d.py:82-83, SPART.py:461-466; the reference's
- * default is 0.01 each).  flags: 0 or SPART_FLAG_SOIL_SPECTRUM. */
+ * default is 0.01 each).  flags: 0, SPART_FLAG_SOIL_SPECTRUM and / or SPART_FLAG_USER_LIDF. */
 int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_t n, int64_t ld,
                            int32_t flags, double rho_thermal, double tau_thermal,
                            void* workspace_dev, double* out_dev, void* stream);

@@ -615,14 +615,16 @@ def srf_convolve(spectrum, opt, sensor):
 
 
 def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_canopy=False, soil_rdry=None,
-                band_mode="interp"):
+                band_mode="interp", lidf=None):
     """SPART(...).run() (SPART.py:162-269) for a batch -> [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
 
     `sensor` is a sensor name or a sensorinfo dict.  faithful=True evaluates the whole
     2162-wavelength spectrum and calls np.interp / the gather-based SRF convolution like
     the reference does; faithful=False evaluates only the wavelengths np.interp touches
     and uses the linearity of the SRF convolution in Ea (identical to ~1e-15).
-    return_canopy=True also returns the band-sampled canopy reflectances [n, nb, 4]."""
+    return_canopy=True also returns the band-sampled canopy reflectances [n, nb, 4].
+    lidf [n, 13]: a leaf inclination distribution assigned to CanopyStructure.lidf after construction, which
+    SAILH then uses as is (sailh.py:81-97 read canopy.lidf); default band mode only."""
     params = np.atleast_2d(np.asarray(params, dtype=np.float64))
     opt = opt or load_optical()
     if isinstance(sensor, str):
@@ -644,7 +646,7 @@ def spart_bands(params, sensor, opt=None, faithful=False, expint=_exp1, return_c
         idx = np.concatenate([lo, hi])
         refl, tran, _ = prospect(params[:, CAB:CBC + 1], opt, idx, expint=expint)
         rwet, _ = bsm(params[:, SOIL_B:FILM + 1], opt, idx, rdry_user=soil_rdry)
-        r4 = sailh(rwet, refl, tran, params[:, LAI:HOT_Q + 1], params[:, SZA:RAA + 1])
+        r4 = sailh(rwet, refl, tran, params[:, LAI:HOT_Q + 1], params[:, SZA:RAA + 1], lidf=lidf)
         nb = lo.shape[0]
         rv = {}
         for name, r in zip(("rso", "rdo", "rsd", "rdd"), r4):

@@ -238,6 +238,9 @@ constexpr int kSampleThreads = 128;
 constexpr int kFlagUniform = 1;
 // internal launch flag: LIDFa and LIDFb are broadcast rows, the twelve F values were computed once (element 0)
 constexpr int kFlagLidfBcast = 1 << 30;
+// internal launch flag: the rows hold a caller-supplied leaf inclination distribution lidf_0..lidf_12 themselves
+// (SPART_FLAG_USER_LIDF, spart_set_lidf) instead of the cumulative values F_1..F_12 of lidf_kernel
+constexpr int kFlagLidfDirect = 1 << 29;
 constexpr uint32_t kLidfRows = (1u << P_LIDFA) | (1u << P_LIDFB);
 constexpr uint32_t kGeometryRows = (1u << P_SZA) | (1u << P_VZA) | (1u << P_RAA);
 
@@ -589,7 +592,7 @@ __device__ __forceinline__ void warp_lidf(const double* sA, const double* sB, do
 
 // workspace rows: the per-sample record followed by the 12 cumulative leaf-angle values
 constexpr int kRowF = R_COUNT;
-constexpr int kWsRows = R_COUNT + 12;
+constexpr int kWsRows = R_COUNT + 13;     // (the 13th row is used by a caller-supplied distribution only)
 
 #ifndef SPART_LIDF_THREADS
 #define SPART_LIDF_THREADS 128
@@ -1047,6 +1050,14 @@ __device__ __forceinline__ void smac_angle_scalars(double us, double uv, double 
   o[7] = us * uv * rcp_fast(us + uv);
 }
 
+// spart_set_lidf: a caller-supplied leaf inclination distribution [n][13] -> the 13 leaf-angle rows of a workspace
+__global__ void lidf_store_kernel(const double* __restrict__ lidf, int64_t n, double* __restrict__ ws) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+#pragma unroll
+  for (int i = 0; i < 13; ++i) ws[(size_t)(kRowF + i) * n + s] = lidf[s * 13 + i];
+}
+
 // Kernel 2, one thread per sample: everything else that does not depend on wavelength or
 // band.  With uniform_geometry != 0 all samples share sun/observer angles (a look-up table
 // for one acquisition geometry): the 13-class volume-scattering terms are then evaluated
@@ -1134,11 +1145,13 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
   // 13 leaf-inclination classes, dotted with lidf (sailh.py:81-97)
   double k = 0.0, K = 0.0, bf = 0.0, sob = 0.0, sof = 0.0;
   if (uniform_geometry) {
+    const bool direct = (flags & kFlagLidfDirect) != 0;
+    const double F12 = direct ? rec[(size_t)(kRowF + 12) * n + sF] : 1.0;
     double Fprev = 0.0;
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
-      const double Fi = (i < 12) ? F[i < 12 ? i : 0] : 1.0;
-      const double lidf = Fi - Fprev;
+      const double Fi = (i < 12) ? F[i < 12 ? i : 0] : F12;
+      const double lidf = direct ? Fi : Fi - Fprev;       // sailh.py:395: lidf = diff(F)
       Fprev = Fi;
       k += s_cls[i][0] * lidf;
       K += s_cls[i][1] * lidf;
@@ -1147,13 +1160,15 @@ geometry_kernel(const Params P, int64_t n, double* __restrict__ rec, int flags) 
       sof += s_cls[i][3] * lidf;
     }
   } else {
+    const bool direct = (flags & kFlagLidfDirect) != 0;
+    const int last = direct ? 12 : 11;          // rows to fetch
     double Fprev = 0.0;
     double Fnext = rec[(size_t)kRowF * n + sF];
 #pragma unroll 1
     for (int i = 0; i < 13; ++i) {
-      const double Fi = (i < 12) ? Fnext : 1.0;
-      if (i < 11) Fnext = rec[(size_t)(kRowF + i + 1) * n + sF];   // in flight during volscatt_class
-      const double lidf = Fi - Fprev;
+      const double Fi = (i <= last) ? Fnext : 1.0;
+      if (i < last) Fnext = rec[(size_t)(kRowF + i + 1) * n + sF];   // in flight during volscatt_class
+      const double lidf = direct ? Fi : Fi - Fprev;                  // sailh.py:395: lidf = diff(F)
       Fprev = Fi;
       double chi_s, chi_o, frho, ftau;
       volscatt_class(sin_tts, cos_tts, sin_tto, cos_tto, psi_rad, sin_psi, cos_psi, c_sin_ttli[i], c_cos_ttli[i], chi_s,
@@ -2290,7 +2305,7 @@ static int launch_lidf(const Params& P, int64_t n_batch, double* ws, cudaStream_
 
 static int launch_geometry(const Params& P, int64_t n, double* ws, int kflags, cudaStream_t st) {
   const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
-  if ((P.bc & kLidfRows) == kLidfRows) kflags |= kFlagLidfBcast;
+  if ((P.bc & kLidfRows) == kLidfRows && !(kflags & kFlagLidfDirect)) kflags |= kFlagLidfBcast;
   geometry_kernel<<<blocks, kSampleThreads, 0, st>>>(P, n, ws, kflags);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -2308,7 +2323,7 @@ static int check_batch(const SpartCtx* ctx, const void* params, int64_t n, int64
 }
 
 static const int kKnownFlags = SPART_FLAG_SOIL_SPECTRUM | SPART_FLAG_SRF_BANDS | SPART_FLAG_REUSE_RECORD |
-                               SPART_FLAG_F32_IO | SPART_FLAG_COMPACT_OUT;
+                               SPART_FLAG_F32_IO | SPART_FLAG_COMPACT_OUT | SPART_FLAG_USER_LIDF;
 
 // flag / precision combinations shared by the device and the host entry point
 static int check_mode(const SpartCtx* ctx, int32_t sensor, int32_t precision, int32_t flags, const char* who) {
@@ -2318,6 +2333,10 @@ static int check_mode(const SpartCtx* ctx, int32_t sensor, int32_t precision, in
   if (flags & ~kKnownFlags) return fail(SPART_EINVAL, "%s: unknown flag bit", who);
   if ((flags & SPART_FLAG_F32_IO) && precision != SPART_FP32)
     return fail(SPART_EINVAL, "%s: SPART_FLAG_F32_IO needs SPART_FP32", who);
+  if ((flags & SPART_FLAG_USER_LIDF) && precision != SPART_FP64)
+    return fail(SPART_EINVAL, "%s: SPART_FLAG_USER_LIDF needs SPART_FP64", who);
+  if ((flags & SPART_FLAG_USER_LIDF) && (flags & SPART_FLAG_REUSE_RECORD))
+    return fail(SPART_EINVAL, "%s: SPART_FLAG_USER_LIDF and SPART_FLAG_REUSE_RECORD exclude each other", who);
   if (flags & SPART_FLAG_SRF_BANDS) {
     if (precision != SPART_FP64) return fail(SPART_EINVAL, "%s: SRF band mode needs SPART_FP64", who);
     if (!ctx->srf[sensor].pair_w) return fail(SPART_EINVAL, "%s: this sensor was created without SRF tables", who);
@@ -2380,12 +2399,13 @@ static int forward_bands_impl(const SpartCtx* ctx, int32_t sensor, const void* p
   const bool compact = (flags & SPART_FLAG_COMPACT_OUT) != 0;
   // one sun / observer geometry for the whole batch by construction: rows 19..21 are broadcast rows
   const bool uniform = (broadcast_rows & kGeometryRows) == kGeometryRows;
-  const int kflags = (flags & SPART_FLAG_SOIL_SPECTRUM) | (uniform ? kFlagUniform : 0);
+  const bool user_lidf = (flags & SPART_FLAG_USER_LIDF) != 0;   // the workspace holds the caller's distribution
+  const int kflags = (flags & SPART_FLAG_SOIL_SPECTRUM) | (uniform ? kFlagUniform : 0) | (user_lidf ? kFlagLidfDirect : 0);
   if (prof) CUDA_TRY(cudaEventRecord(pe.e[0], st));
   if (precision == SPART_FP64) {
     const Params P{(const double*)params_dev, ld, broadcast_rows, (const double*)params_bc_dev};
     double* out = (double*)out_dev;
-    if (!reuse) {
+    if (!reuse && !user_lidf) {
       NvtxRange r("spart::leaf_angles");
       rc = launch_lidf(P, n, rec, st);
       if (rc) return rc;
@@ -2474,16 +2494,20 @@ int spart_forward_spectrum(const SpartCtx* ctx, const double* params_dev, int64_
                            void* stream) {
   int rc = check_batch(ctx, params_dev, n, ld, 0, workspace_dev, out_dev, "spart_forward_spectrum");
   if (rc) return rc;
-  if (flags & ~SPART_FLAG_SOIL_SPECTRUM) return fail(SPART_EINVAL, "spart_forward_spectrum: unknown flag bit%s");
+  if (flags & ~(SPART_FLAG_SOIL_SPECTRUM | SPART_FLAG_USER_LIDF))
+    return fail(SPART_EINVAL, "spart_forward_spectrum: unknown flag bit%s");
   if (n == 0) return SPART_OK;
   GUARD_DEVICE(ctx->device);
   NvtxRange r("spart::spectrum");
   cudaStream_t st = (cudaStream_t)stream;
   double* rec = (double*)workspace_dev;
   const Params P{params_dev, ld, 0u};
-  rc = launch_lidf(P, n, rec, st);
-  if (rc) return rc;
-  rc = launch_geometry(P, n, rec, flags & SPART_FLAG_SOIL_SPECTRUM, st);
+  const bool user_lidf = (flags & SPART_FLAG_USER_LIDF) != 0;     // spart_set_lidf filled the workspace
+  if (!user_lidf) {
+    rc = launch_lidf(P, n, rec, st);
+    if (rc) return rc;
+  }
+  rc = launch_geometry(P, n, rec, (flags & SPART_FLAG_SOIL_SPECTRUM) | (user_lidf ? kFlagLidfDirect : 0), st);
   if (rc) return rc;
   for (int64_t s0 = 0; s0 < n; s0 += 65535) {
     const unsigned ny = (unsigned)((n - s0 < 65535) ? (n - s0) : 65535);
@@ -2668,6 +2692,16 @@ int spart_lut_unpack(const unsigned long long* packed_dev, int64_t m, int64_t* b
   return SPART_OK;
 }
 
+int spart_set_lidf(const double* lidf_dev, int64_t n, void* workspace_dev, void* stream) {
+  if (!lidf_dev || (!workspace_dev && n > 0)) return fail(SPART_EINVAL, "spart_set_lidf: null argument%s");
+  if (n < 0) return fail(SPART_EINVAL, "spart_set_lidf: n < 0%s");
+  if (n == 0) return SPART_OK;
+  lidf_store_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lidf_dev, n, (double*)workspace_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return SPART_OK;
+}
+
 int spart_leafangles(const double* ab_dev, int64_t n, int64_t ld, double* out_dev, void* stream) {
   if (!ab_dev || !out_dev) return fail(SPART_EINVAL, "spart_leafangles: null argument%s");
   if (n < 0 || ld < n) return fail(SPART_EINVAL, "spart_leafangles: need 0 <= n <= ld%s");
@@ -2788,6 +2822,7 @@ int spart_forward_bands_host(SpartCtx* ctx, int32_t sensor, const void* params_h
   if (n < 0 || ld < n) return fail(SPART_EINVAL, "%s: need 0 <= n <= ld", who);
   if (broadcast_rows >> SPART_NPAR) return fail(SPART_EINVAL, "%s: broadcast_rows has bits beyond row 26", who);
   if (flags & SPART_FLAG_REUSE_RECORD) return fail(SPART_EINVAL, "%s: SPART_FLAG_REUSE_RECORD is a device-path flag", who);
+  if (flags & SPART_FLAG_USER_LIDF) return fail(SPART_EINVAL, "%s: SPART_FLAG_USER_LIDF is a device-path flag", who);
   int rc = check_mode(ctx, sensor, precision, flags, who);
   if (rc) return rc;
   if (n == 0) return SPART_OK;

@@ -18,6 +18,7 @@ FLAG_SRF_BANDS = 4
 FLAG_REUSE_RECORD = 8
 FLAG_F32_IO = 16
 FLAG_COMPACT_OUT = 32
+FLAG_USER_LIDF = 64
 NKERNELS = 3
 NPAR = 27
 # rows 19..21 (sun zenith, observer zenith, relative azimuth) as broadcast rows = one geometry for
@@ -31,7 +32,7 @@ EXPORTS = (
     "spart_abi_version", "spart_last_error", "spart_device_count", "spart_create", "spart_destroy",
     "spart_workspace_bytes", "spart_forward_bands", "spart_forward_bands_host", "spart_forward_spectrum",
     "spart_smac", "spart_sailh", "spart_lut_workspace_bytes", "spart_lut_nearest", "spart_lut_nearest_tc", "spart_lut_unpack",
-    "spart_leafangles", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_measure_fp64_chain", "spart_launch_count",
+    "spart_leafangles", "spart_set_lidf", "spart_profile_enable", "spart_profile_read", "spart_measure_peaks", "spart_measure_fp64_chain", "spart_launch_count",
 )
 
 
@@ -93,6 +94,7 @@ def load():
     lib.spart_lut_nearest_tc.argtypes = lib.spart_lut_nearest.argtypes
     lib.spart_lut_unpack.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.spart_leafangles.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
+    lib.spart_set_lidf.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
     lib.spart_profile_enable.argtypes = [c_void_p, c_int32]
     lib.spart_profile_read.argtypes = [c_void_p, POINTER(c_double), POINTER(c_int64)]
     lib.spart_measure_peaks.argtypes = [c_int32, POINTER(c_double), POINTER(c_double)]

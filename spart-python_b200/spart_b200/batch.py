@@ -87,7 +87,8 @@ def _pro_warning(params):
 
 
 def run_batch_params(params, sensor, precision="fp64", device=None, out=None, uniform_geometry=False,
-                     soil_spectrum=None, band_mode="interp", broadcast_rows=0, compact=False, warn=False):
+                     soil_spectrum=None, band_mode="interp", broadcast_rows=0, compact=False, warn=False,
+                     lidf=None):
     """params: [27, n] float64 (float32 with precision="fp32": float32 in, float32 out).  CUDA tensor
     in -> CUDA tensor [n, nb, 3] out (asynchronous on the current stream); NumPy array / CPU tensor
     in -> NumPy array out (copies pipelined in the C library).
@@ -102,7 +103,9 @@ def run_batch_params(params, sensor, precision="fp64", device=None, out=None, un
     the sensor's spectral-response-weighted band means (FP64 only).
     compact=True returns a CompactBands (R_TOC, R_TOA and the per-sample ET scale; L_TOA is rebuilt
     bit for bit on demand): two thirds of the bytes on every copy.
-    warn=True emits the reference's PROSPECT-PRO warning once if the batch triggers it."""
+    warn=True emits the reference's PROSPECT-PRO warning once if the batch triggers it.
+    lidf: leaf inclination distribution [n, 13] (or 13 values for the whole batch) used instead of the one
+    derived from LIDFa / LIDFb, like an assigned `CanopyStructure.lidf` in the reference (FP64, one sensor)."""
     if warn:
         _pro_warning(params)
     kw = dict(precision=precision, uniform_geometry=uniform_geometry, soil_spectrum=soil_spectrum,
@@ -117,8 +120,17 @@ def run_batch_params(params, sensor, precision="fp64", device=None, out=None, un
                 return [CompactBands(o.buf.cpu().numpy(), o.n, o.nb, o.conv_ea_f64, o.fp32) for o in outs]
             return [o.cpu().numpy() for o in outs]
         return default_engine(params.device).forward_bands_multi(params, list(sensor), outs=out, **kw)
+    if lidf is not None and isinstance(sensor, (list, tuple)):
+        raise ValueError("lidf= takes one sensor per call")
     if isinstance(params, torch.Tensor) and params.is_cuda:
-        return default_engine(params.device).forward_bands(params, sensor, out=out, **kw)
+        return default_engine(params.device).forward_bands(params, sensor, out=out, lidf=lidf, **kw)
+    if lidf is not None:         # host arrays with an explicit distribution: through the device path
+        eng = default_engine(device)
+        dev = torch.as_tensor(np.ascontiguousarray(params) if not isinstance(params, torch.Tensor) else params).to(eng.device)
+        res = eng.forward_bands(dev, sensor, lidf=lidf, **kw)
+        if compact:
+            return CompactBands(res.buf.cpu().numpy(), res.n, res.nb, res.conv_ea_f64, res.fp32)
+        return res.cpu().numpy()
     return default_engine(device).forward_bands_host(params, sensor, out=out, **kw)
 
 

@@ -205,9 +205,20 @@ class Engine:
         """Device scratch for a batch of n samples (spart_workspace_bytes)."""
         return torch.empty(max(self.lib.spart_workspace_bytes(None, n) // 8, 1), dtype=torch.float64, device=self.device)
 
+    def _set_lidf(self, lidf, n, ws, stream):
+        """Store a caller-supplied leaf inclination distribution [n, 13] in the workspace (spart_set_lidf)."""
+        lidf = torch.as_tensor(lidf, dtype=torch.float64).to(self.device).reshape(-1, 13)
+        if lidf.shape[0] == 1 and n > 1:
+            lidf = lidf.expand(n, 13)
+        if lidf.shape[0] != n:
+            raise ValueError("lidf must have one row of 13 values per sample (or a single row for the whole batch)")
+        lidf = lidf.contiguous()
+        _lib.check(self.lib.spart_set_lidf(lidf.data_ptr(), n, ws.data_ptr(), stream), "spart_set_lidf")
+        return lidf                       # keep alive until the stream has consumed it
+
     def forward_bands(self, params, sensor, out=None, precision="fp64", uniform_geometry=False,
                       soil_spectrum=None, band_mode="interp", broadcast_rows=0, compact=False,
-                      reuse_record=False, workspace=None):
+                      reuse_record=False, workspace=None, lidf=None):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, nb, 3] = (R_TOC, R_TOA, L_TOA).
         Asynchronous on the current torch stream.
 
@@ -219,13 +230,20 @@ class Engine:
         precision="fp32" with float32 params: float32 in, float32 out (SPART_FLAG_F32_IO).
         compact=True: returns a CompactBands (R_TOC, R_TOA + etscale; two thirds of the bytes).
         `out`: result buffer to fill ([n, nb, 3], or flat with out_elems(n, nb, True) elements when
-        compact)."""
+        compact).
+        lidf: a leaf inclination distribution [n, 13] (or one row for the whole batch) used instead of the one
+        derived from LIDFa / LIDFb -- the reference's assigned `CanopyStructure.lidf`; FP64 only."""
         prec = _PRECISION[precision]
         handle, st = self.sensor(sensor, soil_spectrum)
         params, n, ld = self._prep(params, allow_f32=(prec == _lib.FP32))
         f32_io = params.dtype == torch.float32
         mask = self._geometry_mask(params, n, _lib.row_mask(broadcast_rows), uniform_geometry)
         flags = self._flags(soil_spectrum, band_mode, f32_io, compact, reuse_record)
+        if lidf is not None:
+            if prec != _lib.FP64 or reuse_record or n > MAX_SAMPLES_PER_CALL:
+                raise ValueError("lidf= needs precision='fp64', no reuse_record and at most "
+                                 f"{MAX_SAMPLES_PER_CALL} samples per call")
+            flags |= _lib.FLAG_USER_LIDF
         nb = st.n_bands
         elems = out_elems(n, nb, compact)
         if out is None:
@@ -242,6 +260,7 @@ class Engine:
             for s0 in range(0, n, MAX_SAMPLES_PER_CALL):
                 m = min(MAX_SAMPLES_PER_CALL, n - s0)
                 ws = workspace if (workspace is not None and s0 == 0 and m == n) else self.workspace(m)
+                keep = self._set_lidf(lidf, n, ws, stream) if lidf is not None else None      # noqa: F841
                 _lib.check(self.lib.spart_forward_bands(handle, 0, params.data_ptr() + esz * s0, m, ld, mask, prec, flags,
                                                         ws.data_ptr(), out.data_ptr() + esz * s0 * nb * NOUT,
                                                         stream), "spart_forward_bands")
@@ -264,7 +283,7 @@ class Engine:
                                           compact=compact, reuse_record=i > 0, workspace=ws))
         return res
 
-    def forward_spectrum(self, params, out=None, soil_spectrum=None, rho_thermal=0.01, tau_thermal=0.01):
+    def forward_spectrum(self, params, out=None, soil_spectrum=None, rho_thermal=0.01, tau_thermal=0.01, lidf=None):
         """params: CUDA float64 [27, n] -> CUDA float64 [n, 9, 2162]: leaf refl, leaf tran,
         kChlrel, soil refl, soil refl dry, rso, rdo, rsd, rdd.  rho_thermal / tau_thermal: leaf
         reflectance / transmittance beyond 2400 nm (LeafBiology.rho_thermal / tau_thermal)."""
@@ -276,6 +295,9 @@ class Engine:
         flags = _lib.FLAG_SOIL_SPECTRUM if soil_spectrum is not None else 0
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
+            if lidf is not None:
+                keep = self._set_lidf(lidf, n, ws, stream)      # noqa: F841
+                flags |= _lib.FLAG_USER_LIDF
             _lib.check(self.lib.spart_forward_spectrum(handle, params.data_ptr(), n, ld, flags, float(rho_thermal),
                                                        float(tau_thermal), ws.data_ptr(), out.data_ptr(), stream),
                        "spart_forward_spectrum")

@@ -88,7 +88,11 @@ class SPART:
         key = self._sensor_key()
         p = self._params()
         soil = self._soil_spectrum()
-        out = eng.forward_bands_host(p, key, soil_spectrum=soil)[0]            # [nb, 3]
+        if getattr(self.canopy, "lidf_set", False):      # an assigned leaf inclination distribution: device path
+            dev = torch.from_numpy(p).to(eng.device)
+            out = eng.forward_bands(dev, key, soil_spectrum=soil, lidf=self.canopy.lidf[:, 0]).cpu().numpy()[0]
+        else:
+            out = eng.forward_bands_host(p, key, soil_spectrum=soil)[0]            # [nb, 3]
         self.R_TOC = out[:, 0][None, :].copy()
         self.R_TOA = out[:, 1][None, :].copy()
         self.L_TOA = out[:, 2][None, :].copy()
@@ -105,9 +109,11 @@ class SPART:
         if self._spec is None:
             eng = default_engine()
             p = torch.from_numpy(self._params()).to(eng.device)
+            lidf = self.canopy.lidf[:, 0] if getattr(self.canopy, "lidf_set", False) else None
             self._spec = eng.forward_spectrum(p, soil_spectrum=self._soil_spectrum(),
                                               rho_thermal=getattr(self.leafbio, "rho_thermal", 0.01),
-                                              tau_thermal=getattr(self.leafbio, "tau_thermal", 0.01))[0].cpu().numpy()
+                                              tau_thermal=getattr(self.leafbio, "tau_thermal", 0.01),
+                                              lidf=lidf)[0].cpu().numpy()
         return self._spec
 
     @property

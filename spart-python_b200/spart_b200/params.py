@@ -105,7 +105,7 @@ class CanopyStructure:
     """SAILH canopy: LAI, leaf-inclination parameters LIDFa / LIDFb, hot-spot parameter q.
     `nlayers`, `nlincl`, `nlazi` are the SAIL assumptions 60 / 13 / 36.  `lidf` (the
     13-class leaf inclination distribution the reference computes in its constructor) is
-    evaluated on the GPU on first access."""
+    evaluated on the GPU on first access; an assigned `lidf` replaces it, as in the reference."""
 
     def __init__(self, LAI, LIDFa, LIDFb, q):
         self.LAI = LAI
@@ -116,6 +116,7 @@ class CanopyStructure:
         self.nlincl = 13
         self.nlazi = 36
         self._lidf = None
+        self.lidf_set = False          # True once a distribution has been assigned (it then replaces LIDFa / LIDFb)
 
     @property
     def lidf(self):
@@ -126,10 +127,13 @@ class CanopyStructure:
 
     @lidf.setter
     def lidf(self, value):
-        # the reference would use an assigned distribution as is (sailh.py:93-97 read canopy.lidf);
-        # the GPU path always derives it from LIDFa / LIDFb, so an assignment must not pass silently
-        raise NotImplementedError("a user-assigned lidf is not supported: the GPU path derives the leaf "
-                                  "inclination distribution from LIDFa / LIDFb (set those instead)")
+        # the reference uses an assigned distribution as is (sailh.py:81-97 read canopy.lidf); so does the GPU
+        # path (SPART_FLAG_USER_LIDF): LIDFa / LIDFb are then ignored
+        v = np.asarray(value, dtype=np.float64).reshape(-1)
+        if v.shape[0] != 13:
+            raise ValueError("lidf must hold the 13 leaf-inclination classes of sailh.py:49")
+        self._lidf = v[:, None].copy()
+        self.lidf_set = True
 
     def as_row(self):
         return [self.LAI, self.LIDFa, self.LIDFb, self.q]

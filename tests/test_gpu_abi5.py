@@ -230,8 +230,48 @@ def test_thermal_leaf_optics_are_passed_through(env):
     assert (b.leafopt.tran[2001:, 0] == 0.02).all()
     assert np.array_equal(a.canopyopt.rso[:2001], b.canopyopt.rso[:2001])
     assert not np.allclose(a.canopyopt.rso[2001:], b.canopyopt.rso[2001:])
-    with pytest.raises(NotImplementedError):
-        sb.CanopyStructure(3, -0.35, -0.15, 0.05).lidf = np.ones((13, 1)) / 13
+
+
+def test_user_assigned_lidf(env):
+    """An assigned leaf inclination distribution replaces the one derived from LIDFa / LIDFb, as in the
+    reference (canopy.lidf = ...; sailh.py:81-97 read canopy.lidf): golden rows recorded from the unmodified
+    reference, a batch against the oracle, the SPART class, and the spectra."""
+    torch, sb, so = env
+    g = load_golden("user_lidf.npz")
+    P, L, sensor = g["params"], g["lidf"], str(g["sensor"])
+    got = sb.run_batch_params(_dev(torch, P), sensor, lidf=torch.from_numpy(L).cuda()).cpu().numpy()
+    assert relerr(got, g["O2"]) < RTOL64 and relerr(got, g["O1"]) < 5e-8
+    host = sb.run_batch_params(np.ascontiguousarray(P.T), sensor, lidf=L)                 # NumPy in, NumPy out
+    assert np.array_equal(host, got)
+    # a batch: the distribution the kernels would derive themselves, passed explicitly, and a random one
+    P2 = so.synthetic_params(3000, 2, seed=77)
+    own = so.leafangles(P2[:, so.LIDFA], P2[:, so.LIDFB])
+    a = sb.run_batch_params(_dev(torch, P2), "Sentinel2A-MSI", uniform_geometry=True).cpu().numpy()
+    b = sb.run_batch_params(_dev(torch, P2), "Sentinel2A-MSI", uniform_geometry=True, lidf=own).cpu().numpy()
+    assert relerr(b, a) < 1e-9
+    rnd = np.random.default_rng(5).dirichlet(np.ones(13), size=3000)
+    c = sb.run_batch_params(_dev(torch, P2), "Sentinel2A-MSI", uniform_geometry=True, lidf=rnd, compact=True)
+    assert relerr(c.full().cpu().numpy(), so.spart_bands(P2, "Sentinel2A-MSI", lidf=rnd)) < RTOL64
+    one = sb.run_batch_params(_dev(torch, P2), "Sentinel2A-MSI", lidf=rnd[7]).cpu().numpy()  # one row for the batch
+    assert relerr(one, so.spart_bands(P2, "Sentinel2A-MSI", lidf=np.tile(rnd[7], (3000, 1)))) < RTOL64
+    with pytest.raises(ValueError):
+        sb.run_batch_params(_dev(torch, P2), "Sentinel2A-MSI", lidf=rnd, precision="fp32")
+    # the class API
+    p = P[3]
+    canopy = sb.CanopyStructure(*p[15:19])
+    canopy.lidf = L[3]
+    assert canopy.lidf.shape == (13, 1) and np.array_equal(canopy.lidf[:, 0], L[3])
+    sp = sb.SPART(sb.SoilParameters(*p[9:15]), sb.LeafBiology(*p[0:9]), canopy, sb.AtmosphericProperties(*p[22:26]),
+                  sb.Angles(*p[19:22]), sensor, int(p[26]))
+    df = sp.run()
+    assert relerr(np.stack([df["R_TOC"], df["R_TOA"], df["L_TOA"]], axis=1), g["O2"][3]) < RTOL64
+    plain = sb.SPART(sb.SoilParameters(*p[9:15]), sb.LeafBiology(*p[0:9]), sb.CanopyStructure(*p[15:19]),
+                     sb.AtmosphericProperties(*p[22:26]), sb.Angles(*p[19:22]), sensor, int(p[26]))
+    plain.run()
+    assert not np.allclose(sp.canopyopt.rso[:2001], plain.canopyopt.rso[:2001])          # the spectra follow it too
+    assert np.array_equal(sp.leafopt.refl, plain.leafopt.refl)
+    with pytest.raises(ValueError):
+        canopy.lidf = np.ones(12)
 
 
 def test_sensor_contexts_keyed_by_content_and_bounded(env):

@@ -136,3 +136,13 @@ def test_oracle_srf_band_mode_is_the_references_convolution(name, optical):
     got = so.spart_bands(g["params"], str(g["sensor"]), optical, band_mode="srf")
     assert relerr(got, g["O2"]) < 1e-12
     assert relerr(got, g["O1"]) < 5e-8
+
+
+def test_oracle_user_assigned_lidf(optical):
+    """A leaf inclination distribution assigned after construction (canopy.lidf = ...) is used by SAILH as is
+    (sailh.py:81-97): rows recorded from the unmodified reference (tools/make_golden.py::run_userlidf)."""
+    g = load_golden("user_lidf.npz")
+    got = so.spart_bands(g["params"], str(g["sensor"]), optical, lidf=g["lidf"])
+    assert relerr(got, g["O2"]) < 1e-12
+    assert relerr(got, g["O1"]) < 5e-8
+    assert relerr(so.spart_bands(g["params"], str(g["sensor"]), optical), g["O2"]) > 1e-3      # the override matters

@@ -85,6 +85,20 @@ def run_one(task):
     return out, spec
 
 
+def run_userlidf(task):
+    """Reference run with a leaf inclination distribution assigned after construction
+    (canopy.lidf = ..., which SAILH uses as is, sailh.py:81-97).  task = (params[27], lidf[13], sensor, o2)."""
+    import contextlib
+    import io
+    p, lidf, sensor, o2 = task
+    SPART = _ref_modules(o2)
+    soil, leaf, canopy, atm, angles = _objects(SPART, p)
+    canopy.lidf = np.asarray(lidf, dtype=np.float64).reshape(13, 1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        df = SPART.SPART(soil, leaf, canopy, atm, angles, sensor, int(p[26])).run()
+    return np.stack([df["R_TOC"].to_numpy(), df["R_TOA"].to_numpy(), df["L_TOA"].to_numpy()], axis=1)
+
+
 def run_soilfile(task):
     """Reference run with SoilParametersFromFile(ndarray) (bsm.py:155-226)."""
     import contextlib
@@ -205,6 +219,23 @@ def main():
             np.savez_compressed(GOLD / f"soilfile_{sensor.split('-')[0]}.npz", params=P, rdry=rdry,
                                 sensor=np.array(sensor), O1=o1, O2=o2)
         print("soilfile done", flush=True)
+        if args.only:
+            pool.close()
+            return
+
+    # 7b. a user-assigned leaf inclination distribution (canopy.lidf = ...)
+    if args.only in (None, "userlidf"):
+        P = so.synthetic_params(8, 3, seed=63)
+        rng = np.random.default_rng(64)
+        L = rng.dirichlet(np.ones(13), size=8)
+        L[0] = 1.0 / 13                                        # uniform over the classes
+        L[1] = so.leafangles(np.array([-0.35]), np.array([-0.15]))[0]       # spherical, whatever LIDFa / LIDFb say
+        res = {}
+        for o2 in (False, True):
+            outs = pool.map(run_userlidf, [(P[i], L[i], "LANDSAT8-OLI", o2) for i in range(8)])
+            res["O2" if o2 else "O1"] = np.stack(outs)
+        np.savez_compressed(GOLD / "user_lidf.npz", params=P, lidf=L, sensor=np.array("LANDSAT8-OLI"), **res)
+        print("userlidf done", flush=True)
         if args.only:
             pool.close()
             return
