@@ -531,6 +531,39 @@ def measure_e2e(cx, config, params_dev, n, variant, steps=5, precision="fp64"):
                    f"{', precision=fp32' if f32 else ''}) -> host result"}, dst
 
 
+def measure_copy_ceiling(cx, h2d_bytes, d2h_bytes, pieces=16, reps=6):
+    """What the host link of this box sustains for the bytes of one end-to-end step, copies only: h2d_bytes from
+    and d2h_bytes into pinned host memory, both directions at once on two streams, in `pieces` pieces each.  No
+    implementation of the step can be faster; `e2e.value / ceiling` says how close the pipeline gets."""
+    torch = cx.torch
+    hin = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    hout = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    din = torch.empty(h2d_bytes, dtype=torch.uint8, device=cx.dev)
+    dout = torch.empty(d2h_bytes, dtype=torch.uint8, device=cx.dev)
+    s1, s2 = torch.cuda.Stream(device=cx.dev), torch.cuda.Stream(device=cx.dev)
+
+    def both():
+        a, b = h2d_bytes // pieces, d2h_bytes // pieces
+        with torch.cuda.stream(s1):
+            for i in range(pieces):
+                din[i * a:(i + 1) * a].copy_(hin[i * a:(i + 1) * a], non_blocking=True)
+        with torch.cuda.stream(s2):
+            for i in range(pieces):
+                hout[i * b:(i + 1) * b].copy_(dout[i * b:(i + 1) * b], non_blocking=True)
+
+    best = None
+    for r in range(reps + 1):
+        torch.cuda.synchronize()
+        cx.barrier()
+        t0 = time.perf_counter()
+        both()
+        torch.cuda.synchronize()
+        dt = cx.max_over_ranks(time.perf_counter() - t0)
+        if r > 0:
+            best = dt if best is None else min(best, dt)
+    return best
+
+
 def measure_with_gather(cx, config, params, steps, warmup, variant, n_chunks=4):
     """N > 1: the step followed by the gather of every rank's result on rank 0, chunk-pipelined on a side
     stream (spart_b200.distributed.gather_pipelined) and verified on rank 0.  variant: 'full' (FP64
@@ -703,6 +736,12 @@ def run_ours(args):
     e2e_n = n if config in (2, 3) else min(n, 1 << 21 if config == 5 else 1 << 15)
     e2e_steps = max(1, min(args.steps, 5))
     e2e, got = measure_e2e(cx, config, params, e2e_n, "compact", e2e_steps)
+    t_copy = measure_copy_ceiling(cx, e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"])
+    e2e["copy_only_ceiling"] = {
+        "value": cx.world * e2e_n / t_copy, "unit": "simulations/s", "ms_per_step": t_copy * 1e3,
+        "frac": e2e["value"] / (cx.world * e2e_n / t_copy),
+        "note": "the same bytes moved between pinned host memory and the GPU in both directions at once, 16 pieces "
+                "each, no kernels: the host link's ceiling for this step on this box"}
     # same bits as the device path
     chk = eng.forward_bands(params[:, :e2e_n], cx.sensor(cfg["sensors"][0]), broadcast_rows=cfg["bcast"], compact=True)
     assert torch.equal(got[0].to(cx.dev), chk.buf), "host-buffer path disagrees with the device path"
